@@ -1,0 +1,98 @@
+/* mrb200 -- C ABI of the B200-native collision / proximity backend.
+ *
+ * This is the drop-in boundary for the hot path of vhartman/multirobot-pathplanning-benchmark
+ * (per-configuration and per-edge collision queries, their batch variants, and the
+ * distance / nearest-neighbour calls of the planners).  Plain pointers and sizes only; every
+ * data pointer marked `dev` is a CUDA device pointer owned by the caller, `stream` is a
+ * cudaStream_t passed as void*.  All functions return 0 on success and a negative code on
+ * error (mrb200_last_error() gives the text); nothing is ever reported "free" on failure.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository,
+ * P/ = src/multi_robot_multi_goal_planning/):
+ *   BaseProblem.is_collision_free            P/problems/planning_env.py:1724-1734
+ *   BaseProblem.is_collision_free_for_robot  P/problems/planning_env.py:1736-1744
+ *   BaseProblem.is_edge_collision_free       P/problems/planning_env.py:1746-1763
+ *   batch_config_dist / batch_config_cost    P/problems/core/configuration.py:342-349, 437-510
+ *   MultimodalGraph.get_neighbors            P/planners/prm/prm_graph.py:389-549
+ */
+#ifndef MRB200_H
+#define MRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRB200_OK 0
+#define MRB200_ERR_ARG (-1)         /* bad argument / unsupported shape */
+#define MRB200_ERR_BLOB (-2)        /* scene blob magic / version / size mismatch */
+#define MRB200_ERR_CUDA (-3)        /* CUDA runtime error (see mrb200_last_error) */
+#define MRB200_ERR_NO_DEVICE (-4)   /* no CUDA device: there is no CPU fallback */
+
+typedef struct mrb200_scene mrb200_scene_t;       /* primitive scene with per-mode slots */
+typedef struct mrb200_abstract mrb200_abstract_t; /* sphere-agent environment */
+typedef void* mrb200_stream_t;                    /* cudaStream_t */
+
+int mrb200_version(void);
+const char* mrb200_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t mrb200_launch_count(void);
+
+/* FP32 FMA roofline probe (measurement aid for bench.py): runs n_threads threads x iters x 8
+ * dependent-chain FMAs; out_dev holds n_threads floats (pass NULL to only query n_threads). */
+int mrb200_fp32_probe(int iters, float* out_dev, int32_t* n_threads, mrb200_stream_t stream);
+
+/* ---- sphere-agent environment: AbstractEnvironment, P/problems/abstract_env.py:112-354 ----
+ * radii[n_agents]; spheres: n_sph x (dim centre + radius); rects: n_rect x (dim min + dim max).
+ * fp64 throughout, flags bit-identical to the reference on the same inputs. */
+int mrb200_abstract_create(int n_agents, int dim, const double* radii, int n_sph, const double* spheres,
+                           int n_rect, const double* rects, mrb200_abstract_t** out);
+int mrb200_abstract_destroy(mrb200_abstract_t* env);
+/* is_collision_free for a batch (abstract_env.py:255-276): free[i] = 1 iff q[i] is collision free */
+int mrb200_abstract_check_configs(const mrb200_abstract_t* env, const double* q_dev /*[B, n_agents*dim]*/,
+                                  int64_t B, uint8_t* free_dev /*[B]*/, mrb200_stream_t stream);
+/* is_edge_collision_free for a batch (abstract_env.py:301-354).  N_dev nullable (then
+ * N = max(2, int(|q2-q1|_inf / resolution) + 1)); n_max < 0 means N.  first_pos_dev nullable:
+ * position in the reference's binary order of the first colliding sample, -1 if none. */
+int mrb200_abstract_check_edges(const mrb200_abstract_t* env, const double* q1_dev, const double* q2_dev,
+                                int64_t E, double resolution, const int32_t* N_dev, int32_t n_start,
+                                int32_t n_max, int include_endpoints, uint8_t* free_dev,
+                                int32_t* first_pos_dev, mrb200_stream_t stream);
+
+/* ---- primitive scenes (rai-style): rai_env, P/problems/rai_base_env.py:442-836 ----
+ * A scene holds `max_modes` slots; each slot is a compiled scene blob (layout:
+ * multirobot_pathplanning_benchmark_b200/csrc/scene_blob.h) for one mode's kinematic tree
+ * (rai_base_env.py:704-836 set_to_mode). */
+int mrb200_scene_create(int max_modes, mrb200_scene_t** out);
+int mrb200_scene_destroy(mrb200_scene_t* scene);
+/* upload a host blob into a slot and evaluate its static-static pairs on the device */
+int mrb200_scene_set_mode(mrb200_scene_t* scene, int slot, const void* blob_host, size_t nbytes,
+                          mrb200_stream_t stream);
+/* is_collision_free / is_collision_free_np for a batch (rai_base_env.py:442-513):
+ * free[i] = 1 iff total penetration <= tol.  tol < 0 uses the blob's.  pen_dev nullable: total
+ * penetration per configuration (complete only when full_eval != 0, otherwise the kernel may
+ * stop early once a configuration is decided). */
+int mrb200_check_configs(const mrb200_scene_t* scene, int slot, const float* q_dev /*[B, D]*/, int64_t B,
+                         float tol, uint8_t* free_dev, float* pen_dev, int full_eval,
+                         mrb200_stream_t stream);
+/* is_collision_free_for_robot for a batch (rai_base_env.py:515-615): free[i] = 0 iff total
+ * penetration > tol and some penetrating pair involves a `relevant` shape and no `other`
+ * shape.  relevant / other: host arrays of n_shapes bytes (0/1). */
+int mrb200_check_configs_for_robot(const mrb200_scene_t* scene, int slot, const float* q_dev, int64_t B,
+                                   float tol, const uint8_t* relevant_host, const uint8_t* other_host,
+                                   int n_shapes, uint8_t* free_dev, mrb200_stream_t stream);
+/* is_edge_collision_free for a batch (rai_base_env.py:618-676); arguments as for the abstract
+ * variant, endpoints are fp32 and interpolation runs in fp64 like the reference. */
+int mrb200_check_edges(const mrb200_scene_t* scene, int slot, const float* q1_dev, const float* q2_dev,
+                       int64_t E, double resolution, const int32_t* N_dev, int32_t n_start, int32_t n_max,
+                       int include_endpoints, float tol, uint8_t* free_dev, int32_t* first_pos_dev,
+                       mrb200_stream_t stream);
+/* introspection of a slot: D, n_shapes, n_pairs (dynamic), shared memory bytes per CTA */
+int mrb200_scene_info(const mrb200_scene_t* scene, int slot, int32_t* out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

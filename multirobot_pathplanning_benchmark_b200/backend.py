@@ -1,0 +1,236 @@
+"""Tensor-in / tensor-out batch API over the C ABI (include/mrb200.h).
+
+PyTorch is plumbing only: device memory, streams, torch.distributed.  Every method takes
+CUDA tensors, passes raw pointers + the current stream to libmrb200.so and returns CUDA
+tensors; nothing here computes collisions on the host.
+
+Reference calls these replace, batched (P/ = src/multi_robot_multi_goal_planning/ in the
+reference): is_collision_free (P/problems/rai_base_env.py:442-513, abstract_env.py:255-276),
+is_collision_free_for_robot (rai_base_env.py:515-615), is_edge_collision_free
+(rai_base_env.py:618-676, abstract_env.py:301-354).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .scene import CompiledScene
+
+
+def _require_cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class AbstractBackend:
+    """Sphere agents vs sphere / box obstacles (AbstractEnvironment), fp64, bit-exact."""
+
+    def __init__(self, n_agents: int, dim: int, radii: Sequence[float],
+                 spheres: Sequence[Tuple[Sequence[float], float]] = (),
+                 rects_minmax: Sequence[Tuple[Sequence[float], Sequence[float]]] = (), device=None):
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_agents, self.dim = n_agents, dim
+        self.D = n_agents * dim
+        radii = np.ascontiguousarray(radii, np.float64)
+        sph = np.ascontiguousarray([list(c) + [r] for c, r in spheres], np.float64).reshape(-1)
+        rect = np.ascontiguousarray([list(lo) + list(hi) for lo, hi in rects_minmax], np.float64).reshape(-1)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrb200_abstract_create(
+                n_agents, dim, radii.ctypes.data_as(_lib.c_f64p), len(spheres),
+                sph.ctypes.data_as(_lib.c_f64p) if len(spheres) else None, len(rects_minmax),
+                rect.ctypes.data_as(_lib.c_f64p) if len(rects_minmax) else None, C.byref(h)), "abstract_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.mrb200_abstract_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def check_configs(self, q: torch.Tensor) -> torch.Tensor:
+        """q [B, D] float64 cuda -> bool [B], True = collision free."""
+        q = _require_cuda(q, torch.float64, "q")
+        if q.dim() != 2 or q.shape[1] != self.D:
+            raise ValueError(f"q must be [B, {self.D}]")
+        out = torch.empty(q.shape[0], dtype=torch.uint8, device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.check(self.lib.mrb200_abstract_check_configs(self.handle, q.data_ptr(), q.shape[0], out.data_ptr(),
+                                                              _stream(q.device)), "abstract_check_configs")
+        return out.view(torch.bool)
+
+    def check_edges(self, q1: torch.Tensor, q2: torch.Tensor, resolution: float, N: Optional[torch.Tensor] = None,
+                    n_start: int = 0, n_max: Optional[int] = None, include_endpoints: bool = False):
+        """-> (free bool [E], first colliding position int32 [E], -1 if none)."""
+        q1 = _require_cuda(q1, torch.float64, "q1")
+        q2 = _require_cuda(q2, torch.float64, "q2")
+        if q1.shape != q2.shape or q1.dim() != 2 or q1.shape[1] != self.D:
+            raise ValueError(f"q1, q2 must both be [E, {self.D}]")
+        if N is not None:
+            N = _require_cuda(N, torch.int32, "N")
+        E = q1.shape[0]
+        free = torch.empty(E, dtype=torch.uint8, device=q1.device)
+        first = torch.empty(E, dtype=torch.int32, device=q1.device)
+        with torch.cuda.device(q1.device):
+            _lib.check(self.lib.mrb200_abstract_check_edges(
+                self.handle, q1.data_ptr(), q2.data_ptr(), E, float(resolution), N.data_ptr() if N is not None else None,
+                int(n_start), -1 if n_max is None else int(n_max), int(include_endpoints), free.data_ptr(),
+                first.data_ptr(), _stream(q1.device)), "abstract_check_edges")
+        return free.view(torch.bool), first
+
+
+class SceneBackend:
+    """Primitive scene with per-mode slots (one compiled blob per mode)."""
+
+    def __init__(self, max_modes: int = 64, device=None):
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrb200_scene_create(int(max_modes), C.byref(h)), "scene_create")
+        self.handle = h
+        self.max_modes = max_modes
+        self.compiled = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.mrb200_scene_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def set_mode(self, slot: int, cs: CompiledScene) -> None:
+        blob = np.ascontiguousarray(cs.blob32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrb200_scene_set_mode(self.handle, int(slot), blob.ctypes.data, blob.nbytes,
+                                                      _stream(self.device)), "scene_set_mode")
+        self.compiled[slot] = cs
+
+    def info(self, slot: int):
+        out = (C.c_int32 * 4)()
+        _lib.check(self.lib.mrb200_scene_info(self.handle, int(slot), out), "scene_info")
+        return {"D": out[0], "n_shapes": out[1], "n_pairs": out[2], "smem_bytes": out[3]}
+
+    def _q(self, slot, q, name="q"):
+        q = _require_cuda(q, torch.float32, name)
+        D = self.compiled[slot].dof
+        if q.dim() != 2 or q.shape[1] != D:
+            raise ValueError(f"{name} must be [B, {D}]")
+        return q
+
+    def check_configs(self, slot: int, q: torch.Tensor, tol: Optional[float] = None, return_penetration: bool = False,
+                      full_eval: bool = False, out: Optional[torch.Tensor] = None):
+        """q [B, D] float32 cuda -> bool [B] (True = free) [, total penetration float32 [B]]."""
+        q = self._q(slot, q)
+        B = q.shape[0]
+        flags = out if out is not None else torch.empty(B, dtype=torch.uint8, device=q.device)
+        pen = torch.empty(B, dtype=torch.float32, device=q.device) if return_penetration else None
+        with torch.cuda.device(q.device):
+            _lib.check(self.lib.mrb200_check_configs(
+                self.handle, int(slot), q.data_ptr(), B, -1.0 if tol is None else float(tol), flags.data_ptr(),
+                pen.data_ptr() if pen is not None else None, int(full_eval or return_penetration),
+                _stream(q.device)), "check_configs")
+        f = flags.view(torch.bool)
+        return (f, pen) if return_penetration else f
+
+    def check_configs_for_robot(self, slot: int, q: torch.Tensor, relevant: np.ndarray, other: np.ndarray,
+                                tol: Optional[float] = None) -> torch.Tensor:
+        q = self._q(slot, q)
+        relevant = np.ascontiguousarray(relevant, np.uint8)
+        other = np.ascontiguousarray(other, np.uint8)
+        flags = torch.empty(q.shape[0], dtype=torch.uint8, device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.check(self.lib.mrb200_check_configs_for_robot(
+                self.handle, int(slot), q.data_ptr(), q.shape[0], -1.0 if tol is None else float(tol),
+                relevant.ctypes.data_as(_lib.c_u8p), other.ctypes.data_as(_lib.c_u8p), len(relevant),
+                flags.data_ptr(), _stream(q.device)), "check_configs_for_robot")
+        return flags.view(torch.bool)
+
+    def check_edges(self, slot: int, q1: torch.Tensor, q2: torch.Tensor, resolution: float,
+                    N: Optional[torch.Tensor] = None, n_start: int = 0, n_max: Optional[int] = None,
+                    include_endpoints: bool = False, tol: Optional[float] = None):
+        """-> (free bool [E], first colliding position in binary order int32 [E], -1 if none)."""
+        q1 = self._q(slot, q1, "q1")
+        q2 = self._q(slot, q2, "q2")
+        if q1.shape != q2.shape:
+            raise ValueError("q1 and q2 must have the same shape")
+        if N is not None:
+            N = _require_cuda(N, torch.int32, "N")
+        E = q1.shape[0]
+        free = torch.empty(E, dtype=torch.uint8, device=q1.device)
+        first = torch.empty(E, dtype=torch.int32, device=q1.device)
+        with torch.cuda.device(q1.device):
+            _lib.check(self.lib.mrb200_check_edges(
+                self.handle, int(slot), q1.data_ptr(), q2.data_ptr(), E, float(resolution),
+                N.data_ptr() if N is not None else None, int(n_start), -1 if n_max is None else int(n_max),
+                int(include_endpoints), -1.0 if tol is None else float(tol), free.data_ptr(), first.data_ptr(),
+                _stream(q1.device)), "check_edges")
+        return free.view(torch.bool), first
+
+
+def check_configs_host(be: SceneBackend, slot: int, q_host: torch.Tensor, out_host: torch.Tensor,
+                       chunk: int = 1 << 19, state: Optional[dict] = None) -> None:
+    """Host-buffer entry point (what a CPU-side caller of the reference API uses): q_host
+    [B, D] float32 and out_host [B] uint8, both pinned.  Copies, kernels and read-backs of
+    consecutive chunks overlap on two streams; returns after everything has landed."""
+    if q_host.is_cuda or out_host.is_cuda:
+        raise ValueError("host tensors expected")
+    B, D = q_host.shape
+    dev = be.device
+    st = state if state is not None else {}
+    if st.get("key") != (chunk, D, str(dev)):
+        st["key"] = (chunk, D, str(dev))
+        st["streams"] = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        st["q"] = [torch.empty(chunk, D, dtype=torch.float32, device=dev) for _ in range(2)]
+        st["o"] = [torch.empty(chunk, dtype=torch.uint8, device=dev) for _ in range(2)]
+    cur = torch.cuda.current_stream(dev)
+    for s in st["streams"]:
+        s.wait_stream(cur)
+    for i, start in enumerate(range(0, B, chunk)):
+        n = min(chunk, B - start)
+        k = i & 1
+        with torch.cuda.stream(st["streams"][k]):
+            dq = st["q"][k][:n]
+            dq.copy_(q_host[start:start + n], non_blocking=True)
+            be.check_configs(slot, dq, out=st["o"][k][:n])
+            out_host[start:start + n].copy_(st["o"][k][:n], non_blocking=True)
+    for s in st["streams"]:
+        cur.wait_stream(s)
+
+
+def fp32_fma_peak_tflops(device=None, iters: int = 1 << 15, reps: int = 5) -> float:
+    """Measured FP32 FMA throughput of this GPU (8 independent chains per thread)."""
+    lib = _lib.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    n = C.c_int32()
+    with torch.cuda.device(device):
+        _lib.check(lib.mrb200_fp32_probe(iters, None, C.byref(n), None), "fp32_probe")
+        out = torch.empty(n.value, dtype=torch.float32, device=device)
+        best = 0.0
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.mrb200_fp32_probe(iters, out.data_ptr(), C.byref(n), _stream(device)), "fp32_probe")
+            e1.record()
+            e1.synchronize()
+            best = max(best, n.value * iters * 16.0 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def launch_count() -> int:
+    return int(_lib.load().mrb200_launch_count())

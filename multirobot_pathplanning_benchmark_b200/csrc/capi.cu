@@ -1,0 +1,285 @@
+// extern "C" entry points declared in include/mrb200.h.  No torch types, no allocation on the
+// data path: the caller owns every device buffer and the stream.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/mrb200.h"
+#include "kernels.h"
+#include "scene_blob.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MRB200_ERR_NO_DEVICE : MRB200_ERR_CUDA,
+                "%s: %s", what, cudaGetErrorString(e));
+}
+
+struct ModeSlot {
+    uint32_t* blob = nullptr;  // device
+    int words = 0, D = 0, world_words = 0, n_shapes = 0, n_pairs = 0;
+};
+
+}  // namespace
+
+struct mrb200_scene {
+    std::vector<ModeSlot> slots;
+    int* counter = nullptr;  // device scratch for the edge scheduler
+};
+
+struct mrb200_abstract {
+    mrb::AbstractSceneData data;
+    int* counter = nullptr;
+};
+
+extern "C" {
+
+int mrb200_version(void) { return 100 + MRB_BLOB_VERSION; }
+const char* mrb200_last_error(void) { return g_err; }
+int64_t mrb200_launch_count(void) { return g_launches.load(); }
+
+int mrb200_fp32_probe(int iters, float* out_dev, int32_t* n_threads, mrb200_stream_t stream) {
+    int n = 0;
+    cudaError_t e = mrb::launch_fp32_probe(iters, out_dev, &n, (cudaStream_t)stream);
+    if (n_threads) *n_threads = n;
+    if (e != cudaSuccess) return cuda_fail(e, "fp32_probe");
+    if (out_dev) g_launches++;
+    return MRB200_OK;
+}
+
+// ------------------------------------------------------------------ abstract environment
+int mrb200_abstract_create(int n_agents, int dim, const double* radii, int n_sph, const double* spheres, int n_rect,
+                           const double* rects, mrb200_abstract_t** out) {
+    if (!out || !radii || n_agents < 1 || n_agents > mrb::ABS_MAX_AGENTS || dim < 1 || dim > mrb::ABS_MAX_DIM ||
+        n_sph < 0 || n_sph > mrb::ABS_MAX_OBS || n_rect < 0 || n_rect > mrb::ABS_MAX_OBS || (n_sph && !spheres) ||
+        (n_rect && !rects))
+        return fail(MRB200_ERR_ARG, "abstract_create: unsupported sizes (agents<=%d dim<=%d obstacles<=%d per kind)",
+                    mrb::ABS_MAX_AGENTS, mrb::ABS_MAX_DIM, mrb::ABS_MAX_OBS);
+    auto* env = new mrb200_abstract();
+    memset(&env->data, 0, sizeof(env->data));
+    env->data.n_agents = n_agents;
+    env->data.dim = dim;
+    env->data.n_sph = n_sph;
+    env->data.n_rect = n_rect;
+    for (int i = 0; i < n_agents; i++) env->data.radii[i] = radii[i];
+    for (int o = 0; o < n_sph; o++) {
+        for (int k = 0; k < dim; k++) env->data.sph_c[o][k] = spheres[o * (dim + 1) + k];
+        env->data.sph_r[o] = spheres[o * (dim + 1) + dim];
+    }
+    for (int o = 0; o < n_rect; o++)
+        for (int k = 0; k < dim; k++) {
+            env->data.rect_min[o][k] = rects[o * 2 * dim + k];
+            env->data.rect_max[o][k] = rects[o * 2 * dim + dim + k];
+        }
+    cudaError_t e = cudaMalloc(&env->counter, sizeof(int));
+    if (e != cudaSuccess) {
+        delete env;
+        return cuda_fail(e, "abstract_create");
+    }
+    *out = env;
+    return MRB200_OK;
+}
+
+int mrb200_abstract_destroy(mrb200_abstract_t* env) {
+    if (!env) return MRB200_OK;
+    cudaFree(env->counter);
+    delete env;
+    return MRB200_OK;
+}
+
+int mrb200_abstract_check_configs(const mrb200_abstract_t* env, const double* q, int64_t B, uint8_t* free_dev,
+                                  mrb200_stream_t stream) {
+    if (!env || B < 0 || (B && (!q || !free_dev))) return fail(MRB200_ERR_ARG, "abstract_check_configs: bad argument");
+    if (B == 0) return MRB200_OK;
+    cudaError_t e = mrb::launch_abstract_configs(env->data, q, B, free_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "abstract_check_configs");
+    g_launches++;
+    return MRB200_OK;
+}
+
+int mrb200_abstract_check_edges(const mrb200_abstract_t* env, const double* q1, const double* q2, int64_t E,
+                                double resolution, const int32_t* N_dev, int32_t n_start, int32_t n_max,
+                                int include_endpoints, uint8_t* free_dev, int32_t* first_pos_dev, mrb200_stream_t stream) {
+    if (!env || E < 0 || (E && (!q1 || !q2 || !free_dev)) || n_start < 0 || (!N_dev && !(resolution > 0)))
+        return fail(MRB200_ERR_ARG, "abstract_check_edges: bad argument");
+    if (E == 0) return MRB200_OK;
+    cudaError_t e = mrb::launch_abstract_edges(env->data, q1, q2, E, resolution, N_dev, n_start, n_max, include_endpoints,
+                                               free_dev, first_pos_dev, env->counter, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "abstract_check_edges");
+    g_launches++;
+    return MRB200_OK;
+}
+
+// ------------------------------------------------------------------ primitive scenes
+int mrb200_scene_create(int max_modes, mrb200_scene_t** out) {
+    if (!out || max_modes < 1 || max_modes > 65536) return fail(MRB200_ERR_ARG, "scene_create: bad argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(MRB200_ERR_NO_DEVICE, "scene_create: no CUDA device (%s); there is no CPU fallback",
+                                                cudaGetErrorString(e));
+    auto* sc = new mrb200_scene();
+    sc->slots.resize(max_modes);
+    e = cudaMalloc(&sc->counter, sizeof(int));
+    if (e != cudaSuccess) {
+        delete sc;
+        return cuda_fail(e, "scene_create");
+    }
+    *out = sc;
+    return MRB200_OK;
+}
+
+int mrb200_scene_destroy(mrb200_scene_t* sc) {
+    if (!sc) return MRB200_OK;
+    for (auto& s : sc->slots) cudaFree(s.blob);
+    cudaFree(sc->counter);
+    delete sc;
+    return MRB200_OK;
+}
+
+int mrb200_scene_set_mode(mrb200_scene_t* sc, int slot, const void* blob_host, size_t nbytes, mrb200_stream_t stream) {
+    if (!sc || slot < 0 || slot >= (int)sc->slots.size() || !blob_host) return fail(MRB200_ERR_ARG, "scene_set_mode: bad argument");
+    const uint32_t* h = (const uint32_t*)blob_host;
+    if (nbytes < MRB_HDR_WORDS * 4 || h[MRB_H_MAGIC] != MRB_BLOB_MAGIC || h[MRB_H_VERSION] != MRB_BLOB_VERSION ||
+        (size_t)h[MRB_H_TOTAL_WORDS] * 4 != nbytes || (nbytes & 15))
+        return fail(MRB200_ERR_BLOB, "scene_set_mode: not a version-%d scene blob of %zu bytes", MRB_BLOB_VERSION, nbytes);
+    const int n_shapes = (int)(h[MRB_H_NMOV] + h[MRB_H_NSTA]);
+    if (n_shapes > 256) return fail(MRB200_ERR_ARG, "scene_set_mode: more than 256 collision shapes");
+    ModeSlot& s = sc->slots[slot];
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s.words != (int)h[MRB_H_TOTAL_WORDS]) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode");
+        cudaFree(s.blob);
+        s.blob = nullptr;
+        e = cudaMalloc(&s.blob, nbytes);
+        if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: cudaMalloc");
+    }
+    cudaError_t e = cudaMemcpyAsync(s.blob, blob_host, nbytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: copy");
+    e = cudaStreamSynchronize(st);  // blob_host may be pageable and freed by the caller
+    if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: sync");
+    s.words = (int)h[MRB_H_TOTAL_WORDS];
+    s.D = (int)h[MRB_H_DOF];
+    s.world_words = (int)h[MRB_H_WORLD_WORDS];
+    s.n_shapes = n_shapes;
+    s.n_pairs = 0;
+    for (int t = 0; t < MRB_NUM_PAIR_TYPES; t++) s.n_pairs += (int)h[MRB_H_N_PAIRS + t];
+    if (mrb::scene_smem_bytes(s.words, s.D, s.world_words, s.n_shapes) > 227 * 1024)
+        return fail(MRB200_ERR_ARG, "scene_set_mode: scene needs more than 227 KB of shared memory per CTA");
+    e = mrb::launch_static_penetration(s.blob, st);
+    if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: static pairs");
+    g_launches++;
+    return MRB200_OK;
+}
+
+static const ModeSlot* get_slot(const mrb200_scene_t* sc, int slot) {
+    if (!sc || slot < 0 || slot >= (int)sc->slots.size() || !sc->slots[slot].blob) return nullptr;
+    return &sc->slots[slot];
+}
+
+int mrb200_scene_info(const mrb200_scene_t* sc, int slot, int32_t* out4) {
+    const ModeSlot* s = get_slot(sc, slot);
+    if (!s || !out4) return fail(MRB200_ERR_ARG, "scene_info: empty slot");
+    out4[0] = s->D;
+    out4[1] = s->n_shapes;
+    out4[2] = s->n_pairs;
+    out4[3] = (int32_t)mrb::scene_smem_bytes(s->words, s->D, s->world_words, s->n_shapes);
+    return MRB200_OK;
+}
+
+static int check_configs_impl(const mrb200_scene_t* sc, int slot, const float* q, int64_t B, float tol, uint8_t* free_dev,
+                              float* pen_dev, int full_eval, const mrb::RobotRule& rule, mrb200_stream_t stream) {
+    const ModeSlot* s = get_slot(sc, slot);
+    if (!s) return fail(MRB200_ERR_ARG, "check_configs: empty mode slot %d", slot);
+    if (B < 0 || (B && (!q || !free_dev))) return fail(MRB200_ERR_ARG, "check_configs: bad argument");
+    if (B == 0) return MRB200_OK;
+    mrb::ConfigParams p{};
+    p.blob = s->blob;
+    p.blob_words = s->words;
+    p.D = s->D;
+    p.world_words = s->world_words;
+    p.n_shapes = s->n_shapes;
+    p.q = q;
+    p.B = B;
+    p.tol = tol;
+    p.flags = free_dev;
+    p.pen_out = pen_dev;
+    p.full_eval = full_eval;
+    p.bulk_ok = (((uintptr_t)q) & 15) == 0 && ((s->D * 4 * 32) % 16 == 0);
+    p.rule = rule;
+    cudaError_t e = mrb::launch_check_configs(p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "check_configs");
+    g_launches++;
+    return MRB200_OK;
+}
+
+int mrb200_check_configs(const mrb200_scene_t* sc, int slot, const float* q, int64_t B, float tol, uint8_t* free_dev,
+                         float* pen_dev, int full_eval, mrb200_stream_t stream) {
+    mrb::RobotRule none{};
+    return check_configs_impl(sc, slot, q, B, tol, free_dev, pen_dev, full_eval, none, stream);
+}
+
+int mrb200_check_configs_for_robot(const mrb200_scene_t* sc, int slot, const float* q, int64_t B, float tol,
+                                   const uint8_t* relevant_host, const uint8_t* other_host, int n_shapes, uint8_t* free_dev,
+                                   mrb200_stream_t stream) {
+    const ModeSlot* s = get_slot(sc, slot);
+    if (!s) return fail(MRB200_ERR_ARG, "check_configs_for_robot: empty mode slot %d", slot);
+    if (!relevant_host || !other_host || n_shapes != s->n_shapes)
+        return fail(MRB200_ERR_ARG, "check_configs_for_robot: need %d shape flags", s->n_shapes);
+    mrb::RobotRule rule{};
+    rule.enabled = 1;
+    for (int i = 0; i < n_shapes; i++) {
+        if (relevant_host[i]) rule.rel[i >> 6] |= 1ull << (i & 63);
+        if (other_host[i]) rule.oth[i >> 6] |= 1ull << (i & 63);
+    }
+    return check_configs_impl(sc, slot, q, B, tol, free_dev, nullptr, 1, rule, stream);
+}
+
+int mrb200_check_edges(const mrb200_scene_t* sc, int slot, const float* q1, const float* q2, int64_t E, double resolution,
+                       const int32_t* N_dev, int32_t n_start, int32_t n_max, int include_endpoints, float tol,
+                       uint8_t* free_dev, int32_t* first_pos_dev, mrb200_stream_t stream) {
+    const ModeSlot* s = get_slot(sc, slot);
+    if (!s) return fail(MRB200_ERR_ARG, "check_edges: empty mode slot %d", slot);
+    if (E < 0 || (E && (!q1 || !q2 || !free_dev)) || n_start < 0 || (!N_dev && !(resolution > 0)))
+        return fail(MRB200_ERR_ARG, "check_edges: bad argument");
+    if (E == 0) return MRB200_OK;
+    mrb::EdgeParams p{};
+    p.blob = s->blob;
+    p.blob_words = s->words;
+    p.D = s->D;
+    p.world_words = s->world_words;
+    p.n_shapes = s->n_shapes;
+    p.q1 = q1;
+    p.q2 = q2;
+    p.E = E;
+    p.resolution = resolution;
+    p.N = N_dev;
+    p.n_start = n_start;
+    p.n_max = n_max;
+    p.include_endpoints = include_endpoints;
+    p.tol = tol;
+    p.flags = free_dev;
+    p.first_pos = first_pos_dev;
+    p.counter = sc->counter;
+    cudaError_t e = mrb::launch_check_edges(p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "check_edges");
+    g_launches++;
+    return MRB200_OK;
+}
+
+}  // extern "C"

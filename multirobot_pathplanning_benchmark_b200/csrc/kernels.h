@@ -1,0 +1,69 @@
+// Internal launch interface between the C-ABI layer (capi.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mrb {
+
+// A6 (is_collision_free_for_robot) shape classification, one bit per shape (<= 256 shapes)
+struct RobotRule {
+    unsigned long long rel[4];  // shape belongs to a queried robot or is a frame of its active task
+    unsigned long long oth[4];  // shape belongs to another robot
+    int enabled;
+};
+
+struct ConfigParams {
+    const uint32_t* blob;  // device, compiled scene for the mode
+    int blob_words, D, world_words, n_shapes;
+    const float* q;  // device [B, D]
+    int64_t B;
+    float tol;        // < 0: use the blob's
+    uint8_t* flags;   // device [B], 1 = collision free
+    float* pen_out;   // device [B] or null
+    int full_eval;    // 1: no early exit (pen_out is then the complete sum)
+    int bulk_ok;      // q is 16-byte aligned: tiles may be fetched with cp.async.bulk
+    RobotRule rule;
+};
+
+struct EdgeParams {
+    const uint32_t* blob;
+    int blob_words, D, world_words, n_shapes;
+    const float* q1;  // device [E, D]
+    const float* q2;  // device [E, D]
+    int64_t E;
+    double resolution;
+    const int32_t* N;  // device [E] or null
+    int n_start, n_max, include_endpoints;
+    float tol;
+    uint8_t* flags;       // device [E], 1 = edge collision free
+    int32_t* first_pos;   // device [E] or null: position (in binary order) of the first colliding sample
+    int* counter;         // device scratch: dynamic edge scheduler
+};
+
+size_t scene_smem_bytes(int blob_words, int D, int world_words, int n_shapes);
+cudaError_t launch_static_penetration(uint32_t* blob, cudaStream_t st);
+cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st);
+cudaError_t launch_check_edges(const EdgeParams& p, cudaStream_t st);
+
+// ---- abstract sphere-agent environment (fp64, bit-exact with the reference) ----
+constexpr int ABS_MAX_AGENTS = 8;
+constexpr int ABS_MAX_DIM = 12;
+constexpr int ABS_MAX_OBS = 6;
+struct AbstractSceneData {
+    int n_agents, dim, n_sph, n_rect;
+    double radii[ABS_MAX_AGENTS];
+    double sph_c[ABS_MAX_OBS][ABS_MAX_DIM];
+    double sph_r[ABS_MAX_OBS];
+    double rect_min[ABS_MAX_OBS][ABS_MAX_DIM];
+    double rect_max[ABS_MAX_OBS][ABS_MAX_DIM];
+};
+cudaError_t launch_abstract_configs(const AbstractSceneData& sc, const double* q, int64_t B, uint8_t* flags, cudaStream_t st);
+cudaError_t launch_abstract_edges(const AbstractSceneData& sc, const double* q1, const double* q2, int64_t E,
+                                  double resolution, const int32_t* N, int n_start, int n_max, int include_endpoints,
+                                  uint8_t* flags, int32_t* first_pos, int* counter, cudaStream_t st);
+
+// out: device [n_threads] floats; call with out == nullptr to query n_threads
+cudaError_t launch_fp32_probe(int iters, float* out, int* n_threads, cudaStream_t st);
+
+}  // namespace mrb

@@ -1,0 +1,611 @@
+"""Host-side scene model and scene-blob compiler.
+
+A `Scene` is a tree of frames (rai `.g` semantics: X_frame = X_parent * rel * J(q)),
+some of which carry a collision primitive.  `compile_blob` flattens it, for one mode,
+into the flat word array the CUDA kernels stage into shared memory (layout in
+csrc/scene_blob.h, mirrored here).  Nothing in this file evaluates collisions.
+
+Reference semantics restated (paths relative to /root/reference,
+P/ = src/multi_robot_multi_goal_planning/):
+  * frame / joint conventions, shapes, `contact` flag: the `.g` models under
+    P/assets/models/rai/ (ur10/ur10.g:9-39, mobile-manipulator-restricted.g:1-68) and
+    the scene builders P/problems/rai/rai_config.py:65-100, 751-839, 2947-3064,
+    3319-3513, 7690-7768.
+  * visual-only (mesh / contact-less) frames never collide: P/problems/rai_base_env.py:234-255.
+  * mode relinking (`attach`, `setContact(-1)`): P/problems/rai_base_env.py:776-810.
+  * the flag rule "sum of penetrations > tolerance": P/problems/rai_base_env.py:460-477.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# ----------------------------------------------------------------------------------
+# small fp64 transform helpers (rotation matrix + translation)
+# ----------------------------------------------------------------------------------
+
+
+def quat_to_mat(q: Sequence[float]) -> np.ndarray:
+    """[w,x,y,z] -> 3x3 (normalised first, as rai does on read)."""
+    w, x, y, z = np.asarray(q, np.float64) / np.linalg.norm(q)
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)],
+    ])
+
+
+def mat_to_quat(R: np.ndarray) -> np.ndarray:
+    t = np.trace(R)
+    if t > 0:
+        s = math.sqrt(t + 1.0) * 2
+        q = [0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s]
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = math.sqrt(1.0 + R[i, i] - R[j, j] - R[k, k]) * 2
+        q = [0.0] * 4
+        q[0] = (R[k, j] - R[j, k]) / s
+        q[1 + i] = 0.25 * s
+        q[1 + j] = (R[j, i] + R[i, j]) / s
+        q[1 + k] = (R[k, i] + R[i, k]) / s
+    q = np.array(q)
+    return q if q[0] >= 0 else -q
+
+
+def axis_angle_mat(axis: Sequence[float], rad: float) -> np.ndarray:
+    a = np.asarray(axis, np.float64)
+    a = a / np.linalg.norm(a)
+    c, s = math.cos(rad), math.sin(rad)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + s * K + (1 - c) * (K @ K)
+
+
+class Tf:
+    """Rigid transform (R, t)."""
+
+    __slots__ = ("R", "t")
+
+    def __init__(self, R=None, t=None):
+        self.R = np.eye(3) if R is None else np.asarray(R, np.float64)
+        self.t = np.zeros(3) if t is None else np.asarray(t, np.float64)
+
+    def __matmul__(self, o: "Tf") -> "Tf":
+        return Tf(self.R @ o.R, self.R @ o.t + self.t)
+
+    def apply(self, p) -> np.ndarray:
+        return self.R @ np.asarray(p, np.float64) + self.t
+
+    def inv(self) -> "Tf":
+        return Tf(self.R.T, -self.R.T @ self.t)
+
+    @staticmethod
+    def from_pose(p: Sequence[float]) -> "Tf":
+        """[x,y,z] or [x,y,z,qw,qx,qy,qz]"""
+        p = list(p)
+        if len(p) == 3:
+            return Tf(None, p)
+        return Tf(quat_to_mat(p[3:7]), p[:3])
+
+    @staticmethod
+    def parse(spec: str) -> "Tf":
+        """rai transformation mini-language: sequence of t(x y z) / d(deg ax ay az) /
+        r(rad ax ay az) / q(w x y z) / T, each applied *relative* to the running frame."""
+        import re
+        X = Tf()
+        for tag, args in re.findall(r"([tdrqET])\s*(?:\(([^)]*)\))?", spec):
+            if tag == "T":
+                continue
+            v = [float(a) for a in args.replace(",", " ").split()]
+            if tag == "t":
+                X = X @ Tf(None, v)
+            elif tag == "d":
+                X = X @ Tf(axis_angle_mat(v[1:4], math.radians(v[0])), None)
+            elif tag == "r":
+                X = X @ Tf(axis_angle_mat(v[1:4], v[0]), None)
+            elif tag == "q":
+                X = X @ Tf(quat_to_mat(v), None)
+            else:
+                raise ValueError(tag)
+        return X
+
+
+JOINT_DOF = {"hingeX": 1, "hingeY": 1, "hingeZ": 1, "transXYPhi": 3, "transX": 1, "transY": 1,
+             "transZ": 1, "rigid": 0}
+JOINT_CODE = {"hingeX": 1, "hingeY": 2, "hingeZ": 3, "transXYPhi": 4, "transX": 5, "transY": 6, "transZ": 7}
+
+CORE_POINT, CORE_SEG, CORE_BOX, CORE_CYLZ = 0, 1, 2, 3
+
+
+def joint_tf(jtype: str, q: np.ndarray) -> Tf:
+    if jtype == "hingeX":
+        return Tf(axis_angle_mat([1, 0, 0], q[0]))
+    if jtype == "hingeY":
+        return Tf(axis_angle_mat([0, 1, 0], q[0]))
+    if jtype == "hingeZ":
+        return Tf(axis_angle_mat([0, 0, 1], q[0]))
+    if jtype == "transXYPhi":
+        return Tf(axis_angle_mat([0, 0, 1], q[2]), [q[0], q[1], 0.0])
+    if jtype == "transX":
+        return Tf(None, [q[0], 0, 0])
+    if jtype == "transY":
+        return Tf(None, [0, q[0], 0])
+    if jtype == "transZ":
+        return Tf(None, [0, 0, q[0]])
+    return Tf()
+
+
+@dataclass
+class Shape:
+    """rai shape conventions: sphere [r]; capsule / cylinder [length, r] along local z;
+    box [x,y,z(,ignored)]; ssBox [x,y,z,r] = box of OUTER size x,y,z rounded by r."""
+    kind: str
+    size: Tuple[float, ...]
+
+    def core(self, planar_z: bool = False):
+        """-> (core_type, radius, local data): every primitive is a sphere-swept core, except
+        upright cylinders in planar scenes (`planar_z`: the axis stays parallel to world z for
+        every configuration), which are exact z-prisms (disc x interval).  Cylinders in general
+        position are modelled as capsules with the same radius and a core segment of the
+        cylinder's length (a superset of the cylinder; rai itself uses a convex mesh)."""
+        k, s = self.kind, self.size
+        if k == "sphere":
+            return CORE_POINT, float(s[0]), {}
+        if k == "cylinder" and planar_z:
+            return CORE_CYLZ, 0.0, {"cyl_r": float(s[1]), "cyl_h": float(s[0]) / 2}
+        if k in ("capsule", "cylinder"):
+            return CORE_SEG, float(s[1]), {"half_len": float(s[0]) / 2}
+        if k == "box":
+            return CORE_BOX, 0.0, {"half": np.asarray(s[:3], np.float64) / 2}
+        if k == "ssBox":
+            r = float(s[3])
+            return CORE_BOX, r, {"half": np.asarray(s[:3], np.float64) / 2 - r}
+        raise ValueError(k)
+
+
+@dataclass
+class Frame:
+    name: str
+    parent: Optional[str]
+    rel: Tf = field(default_factory=Tf)
+    joint: Optional[str] = None          # None = plain frame; "rigid" = link boundary w/o dof
+    limits: Optional[np.ndarray] = None  # (dof, 2)
+    q0: Optional[np.ndarray] = None
+    shape: Optional[Shape] = None
+    contact: int = 0
+    robot: Optional[str] = None          # joint frames: which robot owns these dofs
+
+
+class Scene:
+    """Ordered frame tree (parents are always added before children)."""
+
+    def __init__(self):
+        self.frames: Dict[str, Frame] = {}
+        self.robots: List[str] = []
+
+    # ---- construction -----------------------------------------------------------
+    def add(self, name, parent=None, rel=None, joint=None, limits=None, q0=None, shape=None,
+            size=None, contact=0, robot=None) -> Frame:
+        assert name not in self.frames, name
+        assert parent is None or parent in self.frames, parent
+        if isinstance(rel, str):
+            rel = Tf.parse(rel)
+        elif rel is not None and not isinstance(rel, Tf):
+            rel = Tf.from_pose(rel)
+        dof = JOINT_DOF.get(joint, 0) if joint else 0
+        f = Frame(name, parent, rel or Tf(), joint,
+                  None if limits is None else np.asarray(limits, np.float64).reshape(dof, 2),
+                  None if q0 is None else np.asarray(q0, np.float64).reshape(dof),
+                  None if shape is None else Shape(shape, tuple(size)), contact, robot)
+        if dof and f.q0 is None:
+            f.q0 = np.zeros(dof)
+        self.frames[name] = f
+        if robot is not None and dof and robot not in self.robots:
+            self.robots.append(robot)
+        return f
+
+    def copy(self) -> "Scene":
+        return copy.deepcopy(self)
+
+    # ---- joint vector layout ----------------------------------------------------
+    def dof_frames(self) -> List[Frame]:
+        return [f for f in self.frames.values() if f.joint and JOINT_DOF[f.joint] > 0]
+
+    def q_layout(self) -> Dict[str, Tuple[int, int]]:
+        """joint-frame name -> [start, end) in the flat configuration.  Robots' dofs are
+        contiguous and in `self.robots` order (like C.getJointState() for scenes built
+        robot after robot, rai_base_env.py:214-231)."""
+        out, s = {}, 0
+        for r in self.robots:
+            for f in self.dof_frames():
+                if f.robot == r:
+                    n = JOINT_DOF[f.joint]
+                    out[f.name] = (s, s + n)
+                    s += n
+        for f in self.dof_frames():
+            assert f.name in out, f"joint {f.name} has no robot"
+        return out
+
+    @property
+    def dof(self) -> int:
+        return sum(JOINT_DOF[f.joint] for f in self.dof_frames())
+
+    def robot_slices(self) -> Dict[str, Tuple[int, int]]:
+        lay = self.q_layout()
+        out = {}
+        for r in self.robots:
+            idx = [lay[f.name] for f in self.dof_frames() if f.robot == r]
+            out[r] = (min(a for a, _ in idx), max(b for _, b in idx))
+        return out
+
+    def limits(self) -> np.ndarray:
+        lay = self.q_layout()
+        lim = np.zeros((2, self.dof))
+        for f in self.dof_frames():
+            s, e = lay[f.name]
+            lim[0, s:e] = f.limits[:, 0]
+            lim[1, s:e] = f.limits[:, 1]
+        return lim
+
+    def home(self) -> np.ndarray:
+        lay = self.q_layout()
+        q = np.zeros(self.dof)
+        for f in self.dof_frames():
+            s, e = lay[f.name]
+            q[s:e] = f.q0
+        return q
+
+    # ---- forward kinematics on the host (fp64; used for relinking and tests) -----
+    def fk(self, q: np.ndarray) -> Dict[str, Tf]:
+        lay = self.q_layout()
+        X: Dict[str, Tf] = {}
+        for f in self.frames.values():
+            P = X[f.parent] if f.parent is not None else Tf()
+            T = P @ f.rel
+            if f.name in lay:
+                s, e = lay[f.name]
+                T = T @ joint_tf(f.joint, np.asarray(q[s:e], np.float64))
+            X[f.name] = T
+        return X
+
+    # ---- relinking (mode changes) -----------------------------------------------
+    def attach(self, parent: str, child: str, q: np.ndarray) -> None:
+        """rai `C.attach(parent, child)` at configuration q: child keeps its world pose,
+        hangs on `parent` through a rigid joint; then `setContact(-1)` on the child
+        (rai_base_env.py:801-805)."""
+        X = self.fk(q)
+        rel = X[parent].inv() @ X[child]
+        f = self.frames[child]
+        f.parent, f.rel, f.joint, f.contact = parent, rel, "rigid", -1
+        # keep parents-before-children order
+        fr = self.frames.pop(child)
+        self.frames[child] = fr
+        self._reorder()
+
+    def _reorder(self):
+        done, order = set(), []
+        pending = list(self.frames.values())
+        while pending:
+            rest = []
+            for f in pending:
+                if f.parent is None or f.parent in done:
+                    order.append(f)
+                    done.add(f.name)
+                else:
+                    rest.append(f)
+            assert len(rest) < len(pending), "cycle in frame tree"
+            pending = rest
+        self.frames = {f.name: f for f in order}
+
+    def remove(self, name: str) -> None:
+        kids = [f.name for f in self.frames.values() if f.parent == name]
+        for k in kids:
+            self.remove(k)
+        del self.frames[name]
+
+    # ---- link structure and the collidable-pair rule ------------------------------
+    def link_of(self, name: str) -> str:
+        """rai getUpwardLink(): nearest ancestor-or-self that carries a joint (any type,
+        rigid included), else the root."""
+        f = self.frames[name]
+        while f.joint is None and f.parent is not None:
+            f = self.frames[f.parent]
+        return f.name
+
+    def parent_link(self, link: str) -> Optional[str]:
+        p = self.frames[link].parent
+        return None if p is None else self.link_of(p)
+
+    def can_collide(self, a: str, b: str) -> bool:
+        """Restatement of rai's Shape::canCollideWith (source not in the reference repo;
+        SURVEY.md 8a): contact 0 never collides; shapes on the same link never collide;
+        contact = -k additionally suppresses the pair when the other shape's link is one
+        of the first k ancestor links."""
+        fa, fb = self.frames[a], self.frames[b]
+        if not fa.shape or not fb.shape or fa.contact == 0 or fb.contact == 0:
+            return False
+        la, lb = self.link_of(a), self.link_of(b)
+        if la == lb:
+            return False
+        for (l1, c1, l2) in ((la, fa.contact, lb), (lb, fb.contact, la)):
+            if c1 < 0:
+                p = l1
+                for _ in range(-c1):
+                    p = self.parent_link(p)
+                    if p is None:
+                        break
+                    if p == l2:
+                        return False
+        return True
+
+    def collision_shapes(self) -> List[str]:
+        return [f.name for f in self.frames.values() if f.shape is not None and f.contact != 0]
+
+    def collidable_pairs(self) -> List[Tuple[str, str]]:
+        names = self.collision_shapes()
+        return [(a, b) for i, a in enumerate(names) for b in names[i + 1:] if self.can_collide(a, b)]
+
+    def is_moving(self, name: str) -> bool:
+        f = self.frames[name]
+        while True:
+            if f.joint and JOINT_DOF[f.joint] > 0:
+                return True
+            if f.parent is None:
+                return False
+            f = self.frames[f.parent]
+
+    def robot_of_shape(self, name: str) -> Optional[str]:
+        f = self.frames[name]
+        while True:
+            if f.joint and JOINT_DOF[f.joint] > 0:
+                return f.robot
+            if f.parent is None:
+                return None
+            f = self.frames[f.parent]
+
+
+# ----------------------------------------------------------------------------------
+# blob layout (mirror of csrc/scene_blob.h)
+# ----------------------------------------------------------------------------------
+BLOB_MAGIC = 0x4D524232
+BLOB_VERSION = 4
+HDR_WORDS = 48
+FRAME_WORDS = 16
+SHAPE_WORDS = 20
+NUM_PAIR_TYPES = 8   # (point,point) (point,seg) (seg,seg) (point,box) (seg,box) (box,box) (cylz,cylz) (box,cylz)
+PAIR_TYPE = {(0, 0): 0, (0, 1): 1, (1, 1): 2, (0, 2): 3, (1, 2): 4, (2, 2): 5, (3, 3): 6, (2, 3): 7}
+PAIR_TYPE_NAMES = ["point-point", "point-seg", "seg-seg", "point-box", "seg-box", "box-box", "cylz-cylz", "box-cylz"]
+WORLD_WORDS = {CORE_POINT: 3, CORE_SEG: 6, CORE_BOX: 12, CORE_CYLZ: 3}
+# header word indices
+H_MAGIC, H_VERSION, H_DOF, H_NFRAMES, H_NMOV, H_NSTA, H_WORLD_WORDS, H_NCHAINS = range(8)
+H_OFF_FRAMES, H_OFF_SHAPES, H_OFF_CHAINS, H_OFF_STATIC_PAIRS, H_N_STATIC_PAIRS = 8, 9, 10, 11, 12
+H_TOL, H_STATIC_PEN, H_TOTAL_WORDS, H_NROBOTS = 13, 14, 15, 16
+H_OFF_PAIRS = 20   # [20..27]
+H_N_PAIRS = 28     # [28..35]
+H_OFF_SHAPE_ROBOT = 36  # per-shape robot id (moving shapes: owning robot; static: -1; held: holder)
+
+
+@dataclass
+class CompiledScene:
+    """Result of compile_blob: word arrays (u32 view) for the device (fp32) and for the
+    fp64 oracle, plus bookkeeping the host/bench needs."""
+    blob32: np.ndarray            # uint32
+    blob64: np.ndarray            # uint64 (ints stored as uint64, floats as float64 bits)
+    dof: int
+    n_frames: int
+    n_moving: int
+    n_static: int
+    world_words: int
+    pair_counts: List[int]
+    static_pair_count: int
+    shape_names: List[str]
+    pairs: List[Tuple[str, str]]
+    tol: float
+
+
+def compile_blob(scene: Scene, tol: float) -> CompiledScene:
+    lay = scene.q_layout()
+    X0 = scene.fk(scene.home())  # static frames: any q works
+
+    # --- kinematic chains: one per robot, strictly serial dof-joint paths ---
+    dof_frames = scene.dof_frames()
+
+    def dof_ancestor(name: str, inclusive: bool) -> Optional[str]:
+        f = scene.frames[name]
+        if not inclusive:
+            f = scene.frames[f.parent] if f.parent else None
+        while f is not None:
+            if f.joint and JOINT_DOF[f.joint] > 0:
+                return f.name
+            f = scene.frames[f.parent] if f.parent else None
+        return None
+
+    def chain_rel(from_excl: Optional[str], to_incl: str) -> Tf:
+        """product of `rel` from below `from_excl` down to and including `to_incl`
+        (joint motions of intermediate frames are rigid/identity by construction)."""
+        path = []
+        f = scene.frames[to_incl]
+        while f is not None and f.name != from_excl:
+            path.append(f)
+            f = scene.frames[f.parent] if f.parent else None
+        T = Tf()
+        for fr in reversed(path):
+            T = T @ fr.rel
+        return T
+
+    chains: List[List[str]] = []
+    for r in scene.robots:
+        js = [f.name for f in dof_frames if f.robot == r]
+        for i, j in enumerate(js):
+            anc = dof_ancestor(j, inclusive=False)
+            expect = js[i - 1] if i else None
+            assert anc == expect, (
+                f"robot {r}: joint {j} hangs on {anc}, expected {expect} -- only serial chains "
+                "whose base is static are supported")
+        chains.append(js)
+    frame_ids: Dict[str, int] = {}
+    frame_rows = []
+    chain_rows = []
+    for js in chains:
+        start = len(frame_rows)
+        for i, j in enumerate(js):
+            f = scene.frames[j]
+            A = chain_rel(js[i - 1] if i else None, j)
+            frame_ids[j] = len(frame_rows)
+            frame_rows.append((-1 if i == 0 else frame_ids[js[i - 1]], JOINT_CODE[f.joint], lay[j][0], A))
+        chain_rows.append((start, len(frame_rows)))
+
+    # --- shapes: moving ones sorted by frame id (FK emits them while walking the chain) ---
+    def planar_z(name: str) -> bool:
+        """True iff the frame's z axis is world z for every configuration."""
+        f = scene.frames[name]
+        while f is not None:
+            R = f.rel.R
+            if abs(R[2, 2] - 1) > 1e-9 or abs(R[0, 2]) > 1e-9 or abs(R[1, 2]) > 1e-9:
+                return False
+            if f.joint in ("hingeX", "hingeY"):
+                return False
+            f = scene.frames[f.parent] if f.parent else None
+        return True
+
+    robot_ids = {r: i for i, r in enumerate(scene.robots)}
+    mov, sta = [], []
+    for name in scene.collision_shapes():
+        f = scene.frames[name]
+        core, rad, extra = f.shape.core(planar_z(name))
+        j = dof_ancestor(name, inclusive=True)
+        if j is not None:
+            L = chain_rel(j, name) if name != j else Tf()
+            mov.append((frame_ids[j], name, core, rad, extra, L, robot_ids[scene.frames[j].robot]))
+        else:
+            sta.append((-1, name, core, rad, extra, X0[name], -1))
+    mov.sort(key=lambda s: s[0])
+    shapes = mov + sta
+    shape_idx = {s[1]: i for i, s in enumerate(shapes)}
+    n_mov, n_sta = len(mov), len(sta)
+
+    def shape_data(core, extra, T: Tf) -> List[float]:
+        if core == CORE_POINT:
+            return list(T.t)
+        if core == CORE_SEG:
+            h = extra["half_len"]
+            return list(T.apply([0, 0, -h])) + list(T.apply([0, 0, h]))
+        if core == CORE_CYLZ:
+            return list(T.t) + [extra["cyl_r"], extra["cyl_h"]]
+        return list(T.t) + list(T.R.reshape(-1)) + list(extra["half"])
+
+    woff = 0
+    shape_rows = []
+    for (fid, name, core, rad, extra, T, rob) in shapes:
+        shape_rows.append((core, fid, woff if fid >= 0 else -1, rad, shape_data(core, extra, T), rob))
+        if fid >= 0:
+            woff += WORLD_WORDS[core]
+    world_words = woff
+
+    # --- pairs by core-type; static-static pairs kept apart (constant per mode) ---
+    typed: List[List[Tuple[int, int]]] = [[] for _ in range(NUM_PAIR_TYPES)]
+    static_pairs: List[Tuple[int, int, int]] = []
+    all_pairs = scene.collidable_pairs()
+    for a, b in all_pairs:
+        ia, ib = shape_idx[a], shape_idx[b]
+        ca, cb = shapes[ia][2], shapes[ib][2]
+        if ca > cb:  # order so that core(a) <= core(b)
+            ia, ib, ca, cb = ib, ia, cb, ca
+        if (ca, cb) not in PAIR_TYPE:
+            raise NotImplementedError(f"pair {a}-{b}: an upright cylinder can only meet cylinders and boxes")
+        t = PAIR_TYPE[(ca, cb)]
+        if t == 7 and not (planar_z(shapes[ia][1]) and shapes[ia][3] == 0.0):
+            raise NotImplementedError(f"pair {a}-{b}: upright cylinder vs a tilted or rounded box")
+        if ia >= n_mov and ib >= n_mov:
+            static_pairs.append((t, ia, ib))
+        else:
+            typed[t].append((ia, ib))
+    for t in range(NUM_PAIR_TYPES):
+        typed[t].sort()
+
+    # --- assemble words ---
+    n_shapes = len(shapes)
+    off = HDR_WORDS
+    off_frames = off
+    off += FRAME_WORDS * len(frame_rows)
+    off_shapes = off
+    off += SHAPE_WORDS * n_shapes
+    off_chains = off
+    off += 2 * len(chain_rows)
+    off_pairs = []
+    for t in range(NUM_PAIR_TYPES):
+        off_pairs.append(off)
+        off += len(typed[t])
+    off_static = off
+    off += 3 * len(static_pairs)
+    off_shape_robot = off
+    off += n_shapes
+    total = (off + 3) // 4 * 4   # 16-byte multiple for cp.async.bulk
+
+    ints = np.zeros(total, np.int64)
+    flts = np.zeros(total, np.float64)
+    isf = np.zeros(total, bool)
+
+    def setf(i, v):
+        flts[i] = v
+        isf[i] = True
+
+    def seti(i, v):
+        ints[i] = v
+
+    seti(H_MAGIC, BLOB_MAGIC), seti(H_VERSION, BLOB_VERSION), seti(H_DOF, scene.dof)
+    seti(H_NFRAMES, len(frame_rows)), seti(H_NMOV, n_mov), seti(H_NSTA, n_sta)
+    seti(H_WORLD_WORDS, world_words), seti(H_NCHAINS, len(chain_rows))
+    seti(H_OFF_FRAMES, off_frames), seti(H_OFF_SHAPES, off_shapes), seti(H_OFF_CHAINS, off_chains)
+    seti(H_OFF_STATIC_PAIRS, off_static), seti(H_N_STATIC_PAIRS, len(static_pairs))
+    setf(H_TOL, tol), setf(H_STATIC_PEN, 0.0), seti(H_TOTAL_WORDS, total)
+    seti(H_NROBOTS, len(scene.robots)), seti(H_OFF_SHAPE_ROBOT, off_shape_robot)
+    for t in range(NUM_PAIR_TYPES):
+        seti(H_OFF_PAIRS + t, off_pairs[t]), seti(H_N_PAIRS + t, len(typed[t]))
+    for i, (par, jt, qi, A) in enumerate(frame_rows):
+        b = off_frames + FRAME_WORDS * i
+        sh = [k for k, row in enumerate(shape_rows) if row[1] == i]   # moving shapes are sorted by frame
+        assert not sh or sh == list(range(sh[0], sh[0] + len(sh)))
+        seti(b, par), seti(b + 1, jt), seti(b + 2, qi), seti(b + 3, (sh[0] if sh else 0) | (len(sh) << 16))
+        for k, v in enumerate(list(A.R.reshape(-1)) + list(A.t)):
+            setf(b + 4 + k, v)
+    for i, (core, fid, wo, rad, data, rob) in enumerate(shape_rows):
+        b = off_shapes + SHAPE_WORDS * i
+        seti(b, core), seti(b + 1, fid), seti(b + 2, wo), setf(b + 3, rad)
+        for k in range(SHAPE_WORDS - 4):
+            setf(b + 4 + k, data[k] if k < len(data) else 0.0)
+        seti(off_shape_robot + i, rob)
+    for i, (s, e) in enumerate(chain_rows):
+        seti(off_chains + 2 * i, s), seti(off_chains + 2 * i + 1, e)
+    for t in range(NUM_PAIR_TYPES):
+        for i, (a, b_) in enumerate(typed[t]):
+            seti(off_pairs[t] + i, a | (b_ << 16))
+    for i, (t, a, b_) in enumerate(static_pairs):
+        seti(off_static + 3 * i, t), seti(off_static + 3 * i + 1, a), seti(off_static + 3 * i + 2, b_)
+
+    def build(ftype, itype, utype):
+        w = ints.astype(itype).view(utype).copy()
+        w[isf] = flts[isf].astype(ftype).view(utype)
+        return w
+
+    return CompiledScene(
+        blob32=build(np.float32, np.int32, np.uint32), blob64=build(np.float64, np.int64, np.uint64), dof=scene.dof,
+        n_frames=len(frame_rows), n_moving=n_mov, n_static=n_sta, world_words=world_words,
+        pair_counts=[len(t) for t in typed], static_pair_count=len(static_pairs),
+        shape_names=[s[1] for s in shapes], pairs=all_pairs, tol=tol)
+
+
+# Algorithmic flop convention per pair type: used for roofline.achieved only.
+PAIR_FLOPS = [12, 30, 90, 30, 220, 350, 12, 30]
+FK_FLOPS_PER_FRAME = 85
+
+
+def algorithmic_flops_per_config(cs: CompiledScene) -> int:
+    """W_cfg = W_FK + sum over the mode's collidable pairs of w(type): independent of culling
+    and early exit."""
+    n_transforms = cs.n_frames + cs.n_moving
+    return FK_FLOPS_PER_FRAME * n_transforms + sum(n * w for n, w in zip(cs.pair_counts, PAIR_FLOPS))

@@ -1,0 +1,58 @@
+"""CPU-side checks of the C-ABI library: it builds for sm_100a, loads, and exports every symbol
+include/mrb200.h declares.  No compute call is made (there is no GPU here)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from multirobot_pathplanning_benchmark_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "mrb200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mrb200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    build.build()
+    lib = _lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/mrb200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "ctypes table and header diverge"
+    assert lib.mrb200_version() > 100
+
+
+def test_library_contains_sm100a_code_and_tma():
+    build.build()
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3mrb20check_configs_kernelENS_12ConfigParamsE", _lib.LIB_PATH],
+                          capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass, "scene staging should be a bulk async (TMA) copy"
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.mrb200_scene_create(4, C.byref(h))
+    assert rc != 0 and b"no CPU fallback" in lib.mrb200_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multirobot_pathplanning_benchmark_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+                assert "liboracle" not in txt, f

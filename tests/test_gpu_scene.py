@@ -1,0 +1,136 @@
+"""GPU parity, primitive scenes (BASELINE configs 2-5): hand-written fp32 CUDA FK + narrowphase
+vs the fp64 CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): the collision / no-collision flag is identical for every sample
+whose signed clearance exceeds 1e-5; penetration sums agree to 2e-5."""
+import numpy as np
+import pytest
+import torch
+
+from multirobot_pathplanning_benchmark_b200 import scene as S
+from multirobot_pathplanning_benchmark_b200.scenes import SCENES
+from oracle import oracle_scene as O
+
+pytestmark = pytest.mark.gpu
+MARGIN = 1e-5
+
+
+@pytest.fixture(scope="module")
+def be(cuda_lib):
+    from multirobot_pathplanning_benchmark_b200.backend import SceneBackend
+    b = SceneBackend(max_modes=16)
+    b.scenes = {}
+    for slot, (name, (mk, kw)) in enumerate(SCENES.items()):
+        sc = mk()
+        cs = S.compile_blob(sc, kw["tol"])
+        b.set_mode(slot, cs)
+        b.scenes[name] = (slot, sc, cs, kw)
+    return b
+
+
+def uniform_configs(sc, B, seed):
+    lim = sc.limits()
+    np.random.seed(seed)  # the reference's sampler: np.random.uniform in limits (planning_env.py:1697-1708)
+    return np.random.uniform(lim[0], lim[1], (B, sc.dof)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_config_flags_and_penetration(be, name):
+    slot, sc, cs, kw = be.scenes[name]
+    B = 60_000 if name != "box_stacking" else 30_000
+    q = uniform_configs(sc, B + 7, 0)  # ragged tail tile
+    free, pen = be.check_configs(slot, torch.from_numpy(q).cuda(), return_penetration=True)
+    free, pen = free.cpu().numpy(), pen.cpu().numpy()
+    ofree, open_, omind = O.check_configs(cs.blob64, q.astype(np.float64), nthreads=O.max_threads())
+    m = O.margin(open_, omind, cs.tol)
+    clear = np.abs(m) > MARGIN
+    assert clear.mean() > 0.99
+    assert np.array_equal(free[clear], ofree[clear]), f"{(free != ofree)[clear].sum()} margin-clear flags differ"
+    assert np.max(np.abs(pen - open_)) < 2e-5
+    # the early-exit path must give the same flags as the full evaluation
+    fast = be.check_configs(slot, torch.from_numpy(q).cuda()).cpu().numpy()
+    assert np.array_equal(fast, free)
+    assert 0.01 < free.mean() < 0.99
+
+
+def test_home_and_tolerance_override(be):
+    slot, sc, cs, kw = be.scenes["box_rearrangement"]
+    q = torch.from_numpy(np.tile(sc.home().astype(np.float32), (33, 1))).cuda()
+    assert bool(be.check_configs(slot, q).all())
+    qs = torch.from_numpy(uniform_configs(sc, 20000, 3)).cuda()
+    strict = be.check_configs(slot, qs, tol=0.0).cpu().numpy()
+    loose = be.check_configs(slot, qs, tol=0.05).cpu().numpy()
+    dflt = be.check_configs(slot, qs).cpu().numpy()
+    assert strict.sum() < dflt.sum() < loose.sum()
+    o0 = O.check_configs(cs.blob64, qs.cpu().numpy().astype(np.float64), tol=0.05, nthreads=O.max_threads())
+    clear = np.abs(O.margin(o0[1], o0[2], 0.05)) > MARGIN
+    assert np.array_equal(loose[clear], o0[0][clear])
+
+
+def test_unaligned_and_tiny_batches(be):
+    slot, sc, cs, kw = be.scenes["2d_handover"]
+    q = uniform_configs(sc, 1000, 4)
+    base = torch.from_numpy(np.r_[np.zeros(1, np.float32), q.reshape(-1)]).cuda()
+    qt = base[1:].view(1000, sc.dof)  # 4-byte aligned only -> plain-load path
+    got = be.check_configs(slot, qt).cpu().numpy()
+    want = be.check_configs(slot, torch.from_numpy(q).cuda()).cpu().numpy()
+    assert np.array_equal(got, want)
+    for B in (0, 1, 31, 32, 33):
+        f = be.check_configs(slot, torch.from_numpy(q[:B]).cuda())
+        assert f.shape == (B,) and np.array_equal(f.cpu().numpy(), want[:B])
+
+
+@pytest.mark.parametrize("name", ["2d_handover", "box_rearrangement", "mobile_wall_four", "abstract_like"])
+def test_edges(be, name):
+    slot, sc, cs, kw = be.scenes[name]
+    E = 1500 if name != "box_rearrangement" else 600
+    q1 = uniform_configs(sc, E, 10)
+    q2 = uniform_configs(sc, E, 11)
+    q2[::2] = q1[::2] + np.random.default_rng(1).uniform(-0.15, 0.15, q1[::2].shape).astype(np.float32)
+    res = kw["resolution"]
+    free, first = be.check_edges(slot, torch.from_numpy(q1).cuda(), torch.from_numpy(q2).cuda(), res)
+    free, first = free.cpu().numpy(), first.cpu().numpy()
+    ofree, ofirst, _ = O.check_edges(cs.blob64, q1.astype(np.float64), q2.astype(np.float64), res, nthreads=O.max_threads())
+    agree = free == ofree
+    # an edge may only disagree if one of its interpolated configurations is inside the margin
+    for e in np.nonzero(~agree | (first != ofirst))[0]:
+        N = max(2, int(np.max(np.abs(q1[e].astype(np.float64) - q2[e].astype(np.float64))) / res) + 1)
+        idx = O.binary_indices(N)
+        d = (q2[e].astype(np.float64) - q1[e].astype(np.float64)) / (N - 1)
+        ii = idx[(idx != 0) & (idx != N - 1)].astype(np.float64)
+        qs = q1[e].astype(np.float64)[None] + d[None] * ii[:, None]
+        _, p, md = O.check_configs(cs.blob64, qs)
+        assert np.min(np.abs(O.margin(p, md, cs.tol))) <= MARGIN, f"edge {e}: flags differ with all samples margin-clear"
+    assert agree.mean() > 0.995
+    assert 0.02 < free.mean() < 0.98
+
+
+def test_edge_windows_and_explicit_N(be):
+    slot, sc, cs, kw = be.scenes["2d_handover"]
+    q1, q2 = uniform_configs(sc, 400, 20), uniform_configs(sc, 400, 21)
+    t1, t2 = torch.from_numpy(q1).cuda(), torch.from_numpy(q2).cuda()
+    for (ns, nm, inc) in ((0, 2, False), (2, 12, False), (0, None, True), (10, 20, True)):
+        f, p = be.check_edges(slot, t1, t2, 0.01, n_start=ns, n_max=nm, include_endpoints=inc)
+        of, op, _ = O.check_edges(cs.blob64, q1.astype(np.float64), q2.astype(np.float64), 0.01, n_start=ns,
+                                  n_max=-1 if nm is None else nm, include_endpoints=inc)
+        assert (f.cpu().numpy() == of).mean() > 0.99
+        same = f.cpu().numpy() == of
+        assert np.array_equal(p.cpu().numpy()[same & ~of], op[same & ~of]) or (p.cpu().numpy()[same] == op[same]).mean() > 0.99
+    N = torch.full((400,), 25, dtype=torch.int32, device="cuda")
+    f, _ = be.check_edges(slot, t1, t2, 0.01, N=N)
+    of, _, chk = O.check_edges(cs.blob64, q1.astype(np.float64), q2.astype(np.float64), 0.01, Ns=np.full(400, 25, np.int32))
+    assert (f.cpu().numpy() == of).mean() > 0.99 and chk.max() <= 23
+
+
+def test_for_robot_rule(be):
+    """A6: is_collision_free_for_robot (rai_base_env.py:515-615)."""
+    slot, sc, cs, kw = be.scenes["box_rearrangement"]
+    rel = np.array([1 if sc.robot_of_shape(n) == "a1_" else 0 for n in cs.shape_names], np.uint8)
+    oth = np.array([1 if sc.robot_of_shape(n) == "a2_" else 0 for n in cs.shape_names], np.uint8)
+    q = uniform_configs(sc, 40000, 30)
+    got = be.check_configs_for_robot(slot, torch.from_numpy(q).cuda(), rel, oth).cpu().numpy()
+    ofree, open_, omind = O.check_configs(cs.blob64, q.astype(np.float64), rel=rel, oth=oth, nthreads=O.max_threads())
+    clear = (np.abs(O.margin(open_, omind, cs.tol)) > MARGIN) & (np.abs(omind) > MARGIN)
+    assert np.array_equal(got[clear], ofree[clear])
+    plain = be.check_configs(slot, torch.from_numpy(q).cuda()).cpu().numpy()
+    assert (got >= plain).all() and got.sum() > plain.sum()
