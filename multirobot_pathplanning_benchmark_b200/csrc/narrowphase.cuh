@@ -177,7 +177,7 @@ __device__ __forceinline__ float box_box_sat(const float* cA, const float* RA, c
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-            float l2 = fmaf(-R[i][j], R[i][j], 1.f);
+            float l2 = fmaf(R[i1][j], R[i1][j], R[i2][j] * R[i2][j]);  // |a_i x b_j|^2 without cancellation
             if (l2 >= (float)MRB_SAT_PARALLEL_EPS2) {
                 float ra = fmaf(hA[i1], AR[i2][j], hA[i2] * AR[i1][j]);
                 float rb = fmaf(hB[j1], AR[i][j2], hB[j2] * AR[i][j1]);

@@ -9,7 +9,9 @@
  *           moving shapes first (sorted by frame), then static shapes (data in world coordinates)
  *           data: point c[3] | segment a[3] b[3] | box c[3] R[9] row-major half[3] | cylz c[3] r h
  *   chains  [n_chains * 2]                  { first frame, one past last frame } (serial joint paths)
- *   pairs   8 typed lists of packed (a | b << 16) shape indices, core(a) <= core(b)
+ *           data[15] = radius of the bounding sphere around the centre (segment midpoint, box centre)
+ *   pairs   8 typed lists of packed (a | b << 16 | kind << 28) shape indices, core(a) <= core(b);
+ *           kind = broadphase bound: 0 bounding spheres, 1 / 2 face-normal bound against large box b
  *   static pairs [n * 3]                    { type, a, b }  both shapes static: constant per mode
  *   shape robot  [n_shapes]                 owning robot of a moving shape, -1 for static shapes
  */
@@ -17,7 +19,7 @@
 #define MRB_SCENE_BLOB_H
 
 #define MRB_BLOB_MAGIC 0x4D524232
-#define MRB_BLOB_VERSION 4
+#define MRB_BLOB_VERSION 5
 #define MRB_HDR_WORDS 48
 #define MRB_FRAME_WORDS 16
 #define MRB_SHAPE_WORDS 20
@@ -70,6 +72,6 @@
 #define MRB_H_OFF_SHAPE_ROBOT 36
 
 /* threshold below which a box-box edge-edge SAT axis (|a_i x b_j|^2) is skipped as degenerate */
-#define MRB_SAT_PARALLEL_EPS2 1e-6
+#define MRB_SAT_PARALLEL_EPS2 1e-4
 
 #endif

@@ -38,8 +38,9 @@ struct Smem {
     uint32_t* blob;  // staged scene blob
     float* q[2];     // configuration tiles [TILE][D]
     float* W;        // world shape data [world_words][TILE]
-    float* pen;      // [WARPS][TILE]
-    unsigned* relb;  // [WARPS] ballots of "relevant pair penetrates"
+    unsigned* pen_fx;  // [TILE] fixed-point penetration per configuration
+    unsigned* relf;    // [TILE] "a relevant pair penetrates" (A6 rule)
+    uint32_t* queue;   // [WARPS][QCAP] surviving (configuration, pair) items
     uint8_t* sflag;  // [n_shapes] bit0 = relevant, bit1 = other robot (A6 rule)
     uint64_t* bar;   // [3] mbarriers: blob, q0, q1
     int* misc;       // [40] small broadcast scratch (edge kernel)
@@ -54,8 +55,8 @@ __host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_w
     off[1] = o; o = align16(o + size_t(TILE) * D * 4);
     off[2] = o; o = align16(o + size_t(TILE) * D * 4);
     off[3] = o; o = align16(o + size_t(world_words) * TILE * 4);
-    off[4] = o; o = align16(o + size_t(WARPS) * TILE * 4);
-    off[5] = o; o = align16(o + WARPS * 4);
+    off[4] = o; o = align16(o + size_t(2) * TILE * 4);
+    off[5] = o; o = align16(o + size_t(WARPS) * 64 * 4);
     off[6] = o; o = align16(o + size_t(n_shapes));
     off[7] = o; o = align16(o + 3 * 8);
     off[8] = o; o = align16(o + 40 * 4);
@@ -71,8 +72,9 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int blob_words, int D
     s.q[0] = (float*)(base + off[1]);
     s.q[1] = (float*)(base + off[2]);
     s.W = (float*)(base + off[3]);
-    s.pen = (float*)(base + off[4]);
-    s.relb = (unsigned*)(base + off[5]);
+    s.pen_fx = (unsigned*)(base + off[4]);
+    s.relf = s.pen_fx + TILE;
+    s.queue = (uint32_t*)(base + off[5]);
     s.sflag = (uint8_t*)(base + off[6]);
     s.bar = (uint64_t*)(base + off[7]);
     s.misc = (int*)(base + off[8]);
@@ -163,10 +165,19 @@ __device__ __forceinline__ void fk_phase(const uint32_t* bi, const float* q, flo
                 const int core = bi[srow];
                 const float* L = bf + srow + 4;
                 float* w = W + bi[srow + 2] * TILE + lane;
+                if (core == MRB_CORE_SEG) {  // stored as midpoint + half vector
+                    float pa[3], pb[3];
+                    xform_point(R, t, L, pa, 1);
+                    xform_point(R, t, L + 3, pb, 1);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        w[k * TILE] = 0.5f * (pa[k] + pb[k]);
+                        w[(3 + k) * TILE] = 0.5f * (pb[k] - pa[k]);
+                    }
+                    continue;
+                }
                 xform_point(R, t, L, w, TILE);
-                if (core == MRB_CORE_SEG) {
-                    xform_point(R, t, L + 3, w + 3 * TILE, TILE);
-                } else if (core == MRB_CORE_BOX) {
+                if (core == MRB_CORE_BOX) {
 #pragma unroll
                     for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -179,55 +190,234 @@ __device__ __forceinline__ void fk_phase(const uint32_t* bi, const float* q, flo
 }
 
 // ------------------------------------------------------------------------------------------
-// phase 2: pair loops
+// phase 2: broadphase (lane = configuration, uniform over the pair list) -> per-warp queue of
+// surviving (configuration, pair) items -> exact narrowphase, 32 queued items at a time
 // ------------------------------------------------------------------------------------------
-struct PairCtx {
+constexpr int QCAP = 64;                  // queue entries per warp
+constexpr float PEN_SCALE = 67108864.f;   // penetration accumulates in units of 2^-26 m (order independent)
+constexpr float CULL_SLACK = 1e-3f;       // bounding-volume tests keep everything closer than 1 mm
+
+struct TileCtx {
     const uint32_t* bi;
     const float* bf;
     const float* W;
     const uint8_t* sflag;
+    unsigned* pen_fx;  // [TILE]
+    unsigned* relf;    // [TILE]
+    uint32_t* queue;   // [QCAP], this warp's
     int offS, nmov, lane;
     bool rule;
 
+    __device__ __forceinline__ int row(int s) const { return offS + s * MRB_SHAPE_WORDS; }
+    __device__ __forceinline__ float radius(int s) const { return bf[row(s) + 3]; }
+    __device__ __forceinline__ float bound_r(int s) const { return bf[row(s) + 4 + 15]; }
+    __device__ __forceinline__ const float* rowdata(int s) const { return bf + row(s) + 4; }
+    // world data of shape s for configuration cfg (moving: [word][cfg] in W; static: blob row)
     template <int NW>
-    __device__ __forceinline__ void load(int s, float* out) const {
-        const int row = offS + s * MRB_SHAPE_WORDS;
-        if (s < nmov) {  // warp-uniform
-            const float* p = W + bi[row + 2] * TILE + lane;
+    __device__ __forceinline__ void load(int s, int cfg, float* out) const {
+        const int r = row(s);
+        const bool mov = s < nmov;
+        const float* p = mov ? W + bi[r + 2] * TILE + cfg : bf + r + 4;
+        const int st = mov ? TILE : 1;
 #pragma unroll
-            for (int k = 0; k < NW; k++) out[k] = p[k * TILE];
-        } else {
-            const float* p = bf + row + 4;
-#pragma unroll
-            for (int k = 0; k < NW; k++) out[k] = p[k];
-        }
+        for (int k = 0; k < NW; k++) out[k] = p[k * st];
     }
-    __device__ __forceinline__ float radius(int s) const { return bf[offS + s * MRB_SHAPE_WORDS + 3]; }
-    __device__ __forceinline__ const float* rowdata(int s) const { return bf + offS + s * MRB_SHAPE_WORDS + 4; }
-    __device__ __forceinline__ bool relevant(int a, int b) const {
-        const unsigned f = sflag[a] | sflag[b];
-        return (f & 1u) && !(f & 2u);
+    __device__ __forceinline__ void add_pen(int cfg, int a, int b, float d) const {
+        if (d < 0.f) {
+            atomicAdd(&pen_fx[cfg], (unsigned)fmaf(-d, PEN_SCALE, 0.5f));
+            if (rule) {
+                const unsigned f = sflag[a] | sflag[b];
+                if ((f & 1u) && !(f & 2u)) atomicOr(&relf[cfg], 1u);
+            }
+        }
     }
 };
 
-#define MRB_PAIR_LOOP(TYPE, BODY)                                                            \
-    {                                                                                        \
-        const int n_ = bi[MRB_H_N_PAIRS + (TYPE)], off_ = bi[MRB_H_OFF_PAIRS + (TYPE)];      \
-        const int lo_ = (n_ * warp) / WARPS, hi_ = (n_ * (warp + 1)) / WARPS;                \
-        int prev_a = -1;                                                                     \
-        (void)prev_a;                                                                        \
-        for (int i_ = lo_; i_ < hi_; ++i_) {                                                 \
-            const uint32_t pk_ = bi[off_ + i_];                                              \
-            const int a = pk_ & 0xffff, b = pk_ >> 16;                                       \
-            float d;                                                                         \
-            BODY;                                                                            \
-            if (d < 0.f) {                                                                   \
-                pen -= d;                                                                    \
-                if (ctx.rule && ctx.relevant(a, b)) relpen = true;                           \
-            }                                                                                \
-            if (early && ((i_ & 7) == 7) && __all_sync(FULL, pen > tol)) goto pairs_done;    \
-        }                                                                                    \
+// segments live in W as (midpoint, half vector); static blob rows hold (a, b)
+__device__ __forceinline__ void load_seg(const TileCtx& c, int s, int cfg, float* ab) {
+    float v[6];
+    c.load<6>(s, cfg, v);
+    if (s < c.nmov) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ab[k] = v[k] - v[3 + k]; ab[3 + k] = v[k] + v[3 + k]; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) ab[k] = v[k];
     }
+}
+__device__ __forceinline__ void load_centre(const TileCtx& c, int s, int core, int cfg, float* ctr, float* hv) {
+    // centre of the bounding sphere (+ half vector for segments)
+    float v[6];
+    if (core == MRB_CORE_SEG) {
+        c.load<6>(s, cfg, v);
+        if (s < c.nmov) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { ctr[k] = v[k]; hv[k] = v[3 + k]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { ctr[k] = 0.5f * (v[k] + v[3 + k]); hv[k] = 0.5f * (v[3 + k] - v[k]); }
+        }
+    } else {
+        c.load<3>(s, cfg, ctr);
+        hv[0] = hv[1] = hv[2] = 0.f;
+    }
+}
+
+template <int T>
+__device__ __forceinline__ float narrow_pair(const TileCtx& c, int a, int b, int cfg) {
+    const float rs = c.radius(a) + c.radius(b);
+    if constexpr (T == MRB_PT_SEG_SEG) {
+        float A[6], B[6];
+        load_seg(c, a, cfg, A);
+        load_seg(c, b, cfg, B);
+        return d_seg_seg(A, B, rs);
+    } else if constexpr (T == MRB_PT_SEG_BOX) {
+        float A[6], B[12];
+        load_seg(c, a, cfg, A);
+        c.load<12>(b, cfg, B);
+        return d_seg_box(A, B, B + 3, c.rowdata(b) + 12, rs);
+    } else if constexpr (T == MRB_PT_POINT_POINT) {
+        float A[3], B[3];
+        c.load<3>(a, cfg, A);
+        c.load<3>(b, cfg, B);
+        return d_point_point(A, B, rs);
+    } else if constexpr (T == MRB_PT_POINT_SEG) {
+        float A[3], B[6];
+        c.load<3>(a, cfg, A);
+        load_seg(c, b, cfg, B);
+        return d_point_seg(A, B, rs);
+    } else if constexpr (T == MRB_PT_POINT_BOX) {
+        float A[3], B[12];
+        c.load<3>(a, cfg, A);
+        c.load<12>(b, cfg, B);
+        return d_point_box(A, B, B + 3, c.rowdata(b) + 12, rs);
+    } else if constexpr (T == MRB_PT_BOX_BOX) {
+        float A[12], B[12];
+        c.load<12>(a, cfg, A);
+        c.load<12>(b, cfg, B);
+        return d_box_box(A, A + 3, c.rowdata(a) + 12, B, B + 3, c.rowdata(b) + 12, rs);
+    } else if constexpr (T == MRB_PT_CYLZ_CYLZ) {
+        float A[3], B[3];
+        c.load<3>(a, cfg, A);
+        c.load<3>(b, cfg, B);
+        return d_cylz_cylz(A, c.rowdata(a)[3], c.rowdata(a)[4], B, c.rowdata(b)[3], c.rowdata(b)[4]);
+    } else {
+        float A[12], B[3];
+        c.load<12>(a, cfg, A);
+        c.load<3>(b, cfg, B);
+        return d_box_cylz(A, A + 3, c.rowdata(a) + 12, B, c.rowdata(b)[3], c.rowdata(b)[4]);
+    }
+}
+
+template <int T>
+__device__ __forceinline__ void drain(const TileCtx& c, int off, uint32_t entry, bool valid) {
+    if (valid) {
+        const int cfg = entry & 31;
+        const uint32_t pk = c.bi[off + (entry >> 5)];
+        const int a = pk & 0xffff, b = (pk >> 16) & 0xfff;
+        c.add_pen(cfg, a, b, narrow_pair<T>(c, a, b, cfg));
+    }
+}
+
+template <int T>
+__device__ __forceinline__ void run_type(const TileCtx& c, int warp, bool skip_decided, unsigned tol_fx) {
+    constexpr int coreA = (T == MRB_PT_SEG_SEG || T == MRB_PT_SEG_BOX) ? MRB_CORE_SEG
+                          : (T == MRB_PT_BOX_BOX || T == MRB_PT_BOX_CYLZ) ? MRB_CORE_BOX
+                                                                         : MRB_CORE_POINT;
+    constexpr int coreB = (T == MRB_PT_SEG_SEG || T == MRB_PT_POINT_SEG) ? MRB_CORE_SEG
+                          : (T == MRB_PT_SEG_BOX || T == MRB_PT_POINT_BOX || T == MRB_PT_BOX_BOX) ? MRB_CORE_BOX
+                                                                                                   : MRB_CORE_POINT;
+    const uint32_t* bi = c.bi;
+    const int n = bi[MRB_H_N_PAIRS + T], off = bi[MRB_H_OFF_PAIRS + T];
+    if (n == 0) return;
+    const int lo = (n * warp) / WARPS, hi = (n * (warp + 1)) / WARPS;
+    const int lane = c.lane;
+    const unsigned lt = (1u << lane) - 1u;
+    int qn = 0, prev_a = -1;
+    float ca[3] = {0.f, 0.f, 0.f}, ha[3] = {0.f, 0.f, 0.f}, ar = 0.f, ra = 0.f;
+    bool decided = false;
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t pk = bi[off + i];
+        const int a = pk & 0xffff, b = (pk >> 16) & 0xfff, kind = pk >> 28;
+        if (a != prev_a) {  // warp-uniform
+            load_centre(c, a, coreA, lane, ca, ha);
+            ar = c.bound_r(a);
+            ra = c.radius(a);
+            prev_a = a;
+            if (skip_decided) decided = c.pen_fx[lane] > tol_fx;
+        }
+        bool pass;
+        if (kind == 0) {  // bounding spheres
+            float cb[3], hb[3];
+            load_centre(c, b, coreB, lane, cb, hb);
+            const float x = ca[0] - cb[0], y = ca[1] - cb[1], z = ca[2] - cb[2];
+            const float rr = ar + c.bound_r(b) + CULL_SLACK;
+            pass = dot3(x, y, z, x, y, z) < rr * rr;
+        } else {  // b is a large box: separating-axis bound along its three face normals
+            float B[12];
+            c.load<12>(b, lane, B);
+            const float* h = c.rowdata(b) + 12;
+            float l[3], e[3];
+            to_box_local(B, B + 3, ca, l);
+            float lb;
+            if (kind == 2) {
+                const float* R = B + 3;
+                e[0] = fabsf(dot3(R[0], R[3], R[6], ha[0], ha[1], ha[2]));
+                e[1] = fabsf(dot3(R[1], R[4], R[7], ha[0], ha[1], ha[2]));
+                e[2] = fabsf(dot3(R[2], R[5], R[8], ha[0], ha[1], ha[2]));
+                lb = fmaxf(fmaxf(fabsf(l[0]) - e[0] - h[0], fabsf(l[1]) - e[1] - h[1]), fabsf(l[2]) - e[2] - h[2]) - ra;
+            } else {
+                lb = fmaxf(fmaxf(fabsf(l[0]) - h[0], fabsf(l[1]) - h[1]), fabsf(l[2]) - h[2]) - ar;
+            }
+            pass = lb - c.radius(b) < CULL_SLACK;
+        }
+        pass = pass && !decided;
+        const unsigned m = __ballot_sync(FULL, pass);
+        if (m) {
+            if (pass) c.queue[qn + __popc(m & lt)] = ((uint32_t)i << 5) | (uint32_t)lane;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= TILE) {
+                const uint32_t entry = c.queue[lane];
+                const uint32_t tail = c.queue[TILE + lane];
+                __syncwarp();
+                qn -= TILE;
+                if (lane < qn) c.queue[lane] = tail;
+                __syncwarp();
+                drain<T>(c, off, entry, true);
+            }
+        }
+    }
+    if (qn > 0) {
+        const uint32_t entry = c.queue[lane];
+        drain<T>(c, off, entry, lane < qn);
+    }
+    __syncwarp();
+}
+
+// cheap planar pair types are evaluated directly (no queue): lane = configuration
+template <int T>
+__device__ __forceinline__ void run_type_direct(const TileCtx& c, int warp) {
+    const uint32_t* bi = c.bi;
+    const int n = bi[MRB_H_N_PAIRS + T], off = bi[MRB_H_OFF_PAIRS + T];
+    const int lo = (n * warp) / WARPS, hi = (n * (warp + 1)) / WARPS;
+    float pen = 0.f;
+    bool rel = false;
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t pk = bi[off + i];
+        const int a = pk & 0xffff, b = (pk >> 16) & 0xfff;
+        const float d = narrow_pair<T>(c, a, b, c.lane);
+        if (d < 0.f) {
+            pen -= d;
+            if (c.rule) {
+                const unsigned f = c.sflag[a] | c.sflag[b];
+                rel = rel || ((f & 1u) && !(f & 2u));
+            }
+        }
+    }
+    if (pen > 0.f) atomicAdd(&c.pen_fx[c.lane], (unsigned)fmaf(pen, PEN_SCALE, 0.5f));
+    if (rel) atomicOr(&c.relf[c.lane], 1u);
+}
 
 // All THREADS threads call this.  On return warp 0 holds, per lane, the configuration's total
 // penetration (return value) and whether a relevant pair penetrates (*relpen_out).
@@ -235,77 +425,32 @@ __device__ __forceinline__ float process_tile(const Smem& sm, const float* q_til
                                               bool* relpen_out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t* bi = sm.blob;
+    const float static_pen = reinterpret_cast<const float*>(bi)[MRB_H_STATIC_PEN];
+    if (warp == WARPS - 1) {
+        sm.pen_fx[lane] = 0u;
+        sm.relf[lane] = 0u;
+    }
     fk_phase(bi, q_tile + lane * D, sm.W, warp, lane);
     __syncthreads();
 
-    PairCtx ctx{bi, reinterpret_cast<const float*>(bi), sm.W, sm.sflag, (int)bi[MRB_H_OFF_SHAPES], (int)bi[MRB_H_NMOV], lane, rule};
-    float pen = 0.f;
-    bool relpen = false;
-    float A[12];
-    float ra = 0.f;
-
-    MRB_PAIR_LOOP(MRB_PT_SEG_SEG, {
-        if (a != prev_a) { ctx.load<6>(a, A); ra = ctx.radius(a); prev_a = a; }
-        float Bv[6];
-        ctx.load<6>(b, Bv);
-        d = d_seg_seg(A, Bv, ra + ctx.radius(b));
-    })
-    MRB_PAIR_LOOP(MRB_PT_SEG_BOX, {
-        if (a != prev_a) { ctx.load<6>(a, A); ra = ctx.radius(a); prev_a = a; }
-        float Bv[12];
-        ctx.load<12>(b, Bv);
-        d = d_seg_box(A, Bv, Bv + 3, ctx.rowdata(b) + 12, ra + ctx.radius(b));
-    })
-    MRB_PAIR_LOOP(MRB_PT_POINT_POINT, {
-        float Bv[3];
-        ctx.load<3>(a, A);
-        ctx.load<3>(b, Bv);
-        d = d_point_point(A, Bv, ctx.radius(a) + ctx.radius(b));
-    })
-    MRB_PAIR_LOOP(MRB_PT_POINT_SEG, {
-        float Bv[6];
-        ctx.load<3>(a, A);
-        ctx.load<6>(b, Bv);
-        d = d_point_seg(A, Bv, ctx.radius(a) + ctx.radius(b));
-    })
-    MRB_PAIR_LOOP(MRB_PT_POINT_BOX, {
-        float Bv[12];
-        ctx.load<3>(a, A);
-        ctx.load<12>(b, Bv);
-        d = d_point_box(A, Bv, Bv + 3, ctx.rowdata(b) + 12, ctx.radius(a) + ctx.radius(b));
-    })
-    MRB_PAIR_LOOP(MRB_PT_BOX_BOX, {
-        float Bv[12];
-        ctx.load<12>(a, A);
-        ctx.load<12>(b, Bv);
-        d = d_box_box(A, A + 3, ctx.rowdata(a) + 12, Bv, Bv + 3, ctx.rowdata(b) + 12, ctx.radius(a) + ctx.radius(b));
-    })
-    MRB_PAIR_LOOP(MRB_PT_CYLZ_CYLZ, {
-        float Bv[3];
-        ctx.load<3>(a, A);
-        ctx.load<3>(b, Bv);
-        d = d_cylz_cylz(A, ctx.rowdata(a)[3], ctx.rowdata(a)[4], Bv, ctx.rowdata(b)[3], ctx.rowdata(b)[4]);
-    })
-    MRB_PAIR_LOOP(MRB_PT_BOX_CYLZ, {
-        float Bv[3];
-        ctx.load<12>(a, A);
-        ctx.load<3>(b, Bv);
-        d = d_box_cylz(A, A + 3, ctx.rowdata(a) + 12, Bv, ctx.rowdata(b)[3], ctx.rowdata(b)[4]);
-    })
-pairs_done:
-    sm.pen[warp * TILE + lane] = pen;
-    const unsigned rb = __ballot_sync(FULL, relpen);
-    if (lane == 0) sm.relb[warp] = rb;
+    const TileCtx ctx{bi, reinterpret_cast<const float*>(bi), sm.W, sm.sflag, sm.pen_fx, sm.relf, sm.queue + warp * QCAP,
+                      (int)bi[MRB_H_OFF_SHAPES], (int)bi[MRB_H_NMOV], lane, rule};
+    // a configuration is decided once its accumulated penetration exceeds tol - static part
+    const float budget = fmaxf(tol - static_pen, 0.f);
+    const unsigned tol_fx = (unsigned)fminf(budget * PEN_SCALE, 4.0e9f);
+    run_type<MRB_PT_SEG_SEG>(ctx, warp, early, tol_fx);
+    run_type<MRB_PT_SEG_BOX>(ctx, warp, early, tol_fx);
+    run_type<MRB_PT_POINT_POINT>(ctx, warp, early, tol_fx);
+    run_type<MRB_PT_POINT_SEG>(ctx, warp, early, tol_fx);
+    run_type<MRB_PT_POINT_BOX>(ctx, warp, early, tol_fx);
+    run_type<MRB_PT_BOX_BOX>(ctx, warp, early, tol_fx);
+    run_type_direct<MRB_PT_CYLZ_CYLZ>(ctx, warp);
+    run_type_direct<MRB_PT_BOX_CYLZ>(ctx, warp);
     __syncthreads();
     float total = 0.f;
     if (warp == 0) {
-        total = reinterpret_cast<const float*>(bi)[MRB_H_STATIC_PEN];
-#pragma unroll
-        for (int w = 0; w < WARPS; w++) total += sm.pen[w * TILE + lane];
-        unsigned r = 0;
-#pragma unroll
-        for (int w = 0; w < WARPS; w++) r |= sm.relb[w];
-        *relpen_out = (r >> lane) & 1u;
+        total = static_pen + (float)sm.pen_fx[lane] * (1.f / PEN_SCALE);
+        *relpen_out = sm.relf[lane] != 0u;
     }
     return total;
 }

@@ -372,10 +372,11 @@ class Scene:
 # blob layout (mirror of csrc/scene_blob.h)
 # ----------------------------------------------------------------------------------
 BLOB_MAGIC = 0x4D524232
-BLOB_VERSION = 4
+BLOB_VERSION = 5
 HDR_WORDS = 48
 FRAME_WORDS = 16
 SHAPE_WORDS = 20
+LARGE_BOX_BOUND = 0.3  # boxes with a bounding radius above this use the face-normal broadphase bound
 NUM_PAIR_TYPES = 8   # (point,point) (point,seg) (seg,seg) (point,box) (seg,box) (box,box) (cylz,cylz) (box,cylz)
 PAIR_TYPE = {(0, 0): 0, (0, 1): 1, (1, 1): 2, (0, 2): 3, (1, 2): 4, (2, 2): 5, (3, 3): 6, (2, 3): 7}
 PAIR_TYPE_NAMES = ["point-point", "point-seg", "seg-seg", "point-box", "seg-box", "box-box", "cylz-cylz", "box-cylz"]
@@ -498,10 +499,24 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
             return list(T.t) + [extra["cyl_r"], extra["cyl_h"]]
         return list(T.t) + list(T.R.reshape(-1)) + list(extra["half"])
 
+    def bound_radius(core, rad, extra) -> float:
+        """radius of the bounding sphere around the shape's centre (segment midpoint, box centre)"""
+        if core == CORE_SEG:
+            return extra["half_len"] + rad
+        if core == CORE_BOX:
+            return float(np.linalg.norm(extra["half"])) + rad
+        if core == CORE_CYLZ:
+            return math.hypot(extra["cyl_r"], extra["cyl_h"])
+        return rad
+
     woff = 0
     shape_rows = []
+    bound_rs = []
     for (fid, name, core, rad, extra, T, rob) in shapes:
-        shape_rows.append((core, fid, woff if fid >= 0 else -1, rad, shape_data(core, extra, T), rob))
+        data = shape_data(core, extra, T)
+        data = data + [0.0] * (15 - len(data)) + [bound_radius(core, rad, extra)]   # data[15] = bounding radius
+        bound_rs.append(data[15])
+        shape_rows.append((core, fid, woff if fid >= 0 else -1, rad, data, rob))
         if fid >= 0:
             woff += WORLD_WORDS[core]
     world_words = woff
@@ -520,10 +535,18 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
         t = PAIR_TYPE[(ca, cb)]
         if t == 7 and not (planar_z(shapes[ia][1]) and shapes[ia][3] == 0.0):
             raise NotImplementedError(f"pair {a}-{b}: upright cylinder vs a tilted or rounded box")
+        # broadphase kind (bits 28..29 of the packed pair): 0 = bounding spheres; when b is a box too
+        # large for its bounding sphere to cull anything, a separating-axis bound along b's face
+        # normals: 1 = a's bounding sphere, 2 = a's core segment
+        kind = 0
+        if t == 5 and bound_rs[ia] > bound_rs[ib]:
+            ia, ib = ib, ia  # box-box: the larger box is b
+        if cb == CORE_BOX and bound_rs[ib] > LARGE_BOX_BOUND and t in (3, 4, 5):
+            kind = 2 if ca == CORE_SEG else 1
         if ia >= n_mov and ib >= n_mov:
             static_pairs.append((t, ia, ib))
         else:
-            typed[t].append((ia, ib))
+            typed[t].append((ia, ib, kind))
     for t in range(NUM_PAIR_TYPES):
         typed[t].sort()
 
@@ -582,8 +605,8 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
     for i, (s, e) in enumerate(chain_rows):
         seti(off_chains + 2 * i, s), seti(off_chains + 2 * i + 1, e)
     for t in range(NUM_PAIR_TYPES):
-        for i, (a, b_) in enumerate(typed[t]):
-            seti(off_pairs[t] + i, a | (b_ << 16))
+        for i, (a, b_, kind) in enumerate(typed[t]):
+            seti(off_pairs[t] + i, a | (b_ << 16) | (kind << 28))
     for i, (t, a, b_) in enumerate(static_pairs):
         seti(off_static + 3 * i, t), seti(off_static + 3 * i + 1, a), seti(off_static + 3 * i + 2, b_)
 

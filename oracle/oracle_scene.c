@@ -217,7 +217,7 @@ static double box_box_sat(const double* A, const double* B) {
         int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
         for (int j = 0; j < 3; j++) {
             int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-            double l2 = 1.0 - R[i][j] * R[i][j];
+            double l2 = R[i1][j] * R[i1][j] + R[i2][j] * R[i2][j]; /* |a_i x b_j|^2 */
             if (l2 < MRB_SAT_PARALLEL_EPS2) continue;
             double ra = hA[i1] * AR[i2][j] + hA[i2] * AR[i1][j];
             double rb = hB[j1] * AR[i][j2] + hB[j2] * AR[i][j1];
@@ -375,7 +375,7 @@ static void eval_config(blob_t b, const double* q, double static_pen, const uint
     for (int t = 0; t < MRB_NUM_PAIR_TYPES; t++) {
         int64_t n = BI(b, MRB_H_N_PAIRS + t), off = BI(b, MRB_H_OFF_PAIRS + t);
         for (int64_t i = 0; i < n; i++) {
-            int64_t pk = BI(b, off + i), a = pk & 0xffff, c = pk >> 16;
+            int64_t pk = BI(b, off + i), a = pk & 0xffff, c = (pk >> 16) & 0xfff;
             double d = pair_distance(t, W + a * 16, W + c * 16, shape_radius(b, a) + shape_radius(b, c));
             if (d < 0) {
                 pen -= d;
