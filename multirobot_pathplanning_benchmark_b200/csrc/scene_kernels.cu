@@ -222,6 +222,21 @@ struct TileCtx {
 #pragma unroll
         for (int k = 0; k < NW; k++) out[k] = p[k * st];
     }
+    // same, for a shape index that is uniform across the warp (lane = configuration): real
+    // branches and plain LDS instead of per-lane pointer selects
+    template <int NW>
+    __device__ __forceinline__ void load_u(int s, float* out) const {
+        const int r = row(s);
+        if (s < nmov) {
+            const float* p = W + bi[r + 2] * TILE + lane;
+#pragma unroll
+            for (int k = 0; k < NW; k++) out[k] = p[k * TILE];
+        } else {
+            const float* p = bf + r + 4;
+#pragma unroll
+            for (int k = 0; k < NW; k++) out[k] = p[k];
+        }
+    }
     __device__ __forceinline__ void add_pen(int cfg, int a, int b, float d) const {
         if (d < 0.f) {
             atomicAdd(&pen_fx[cfg], (unsigned)fmaf(-d, PEN_SCALE, 0.5f));
@@ -245,21 +260,27 @@ __device__ __forceinline__ void load_seg(const TileCtx& c, int s, int cfg, float
         for (int k = 0; k < 6; k++) ab[k] = v[k];
     }
 }
-__device__ __forceinline__ void load_centre(const TileCtx& c, int s, int core, int cfg, float* ctr, float* hv) {
-    // centre of the bounding sphere (+ half vector for segments)
-    float v[6];
-    if (core == MRB_CORE_SEG) {
-        c.load<6>(s, cfg, v);
-        if (s < c.nmov) {
+// bounding-sphere centre (+ half vector of a segment) of a warp-uniform shape index
+template <int CORE, bool WANT_HALF>
+__device__ __forceinline__ void load_centre_u(const TileCtx& c, int s, float* ctr, float* hv) {
+    if constexpr (CORE == MRB_CORE_SEG) {
+        if (s < c.nmov) {  // (midpoint, half vector) in W
+            if constexpr (WANT_HALF) {
+                float v[6];
+                c.load_u<6>(s, v);
 #pragma unroll
-            for (int k = 0; k < 3; k++) { ctr[k] = v[k]; hv[k] = v[3 + k]; }
-        } else {
+                for (int k = 0; k < 3; k++) { ctr[k] = v[k]; hv[k] = v[3 + k]; }
+            } else {
+                c.load_u<3>(s, ctr);
+            }
+        } else {  // static rows hold the end points
+            float v[6];
+            c.load_u<6>(s, v);
 #pragma unroll
             for (int k = 0; k < 3; k++) { ctr[k] = 0.5f * (v[k] + v[3 + k]); hv[k] = 0.5f * (v[3 + k] - v[k]); }
         }
     } else {
-        c.load<3>(s, cfg, ctr);
-        hv[0] = hv[1] = hv[2] = 0.f;
+        c.load_u<3>(s, ctr);
     }
 }
 
@@ -310,7 +331,7 @@ __device__ __forceinline__ float narrow_pair(const TileCtx& c, int a, int b, int
 }
 
 template <int T>
-__device__ __forceinline__ void drain(const TileCtx& c, int off, uint32_t entry, bool valid) {
+__device__ __noinline__ void drain(const TileCtx& c, int off, uint32_t entry, bool valid) {
     if (valid) {
         const int cfg = entry & 31;
         const uint32_t pk = c.bi[off + (entry >> 5)];
@@ -340,7 +361,7 @@ __device__ __forceinline__ void run_type(const TileCtx& c, int warp, bool skip_d
         const uint32_t pk = bi[off + i];
         const int a = pk & 0xffff, b = (pk >> 16) & 0xfff, kind = pk >> 28;
         if (a != prev_a) {  // warp-uniform
-            load_centre(c, a, coreA, lane, ca, ha);
+            load_centre_u<coreA, true>(c, a, ca, ha);
             ar = c.bound_r(a);
             ra = c.radius(a);
             prev_a = a;
@@ -349,13 +370,13 @@ __device__ __forceinline__ void run_type(const TileCtx& c, int warp, bool skip_d
         bool pass;
         if (kind == 0) {  // bounding spheres
             float cb[3], hb[3];
-            load_centre(c, b, coreB, lane, cb, hb);
+            load_centre_u<coreB, false>(c, b, cb, hb);
             const float x = ca[0] - cb[0], y = ca[1] - cb[1], z = ca[2] - cb[2];
             const float rr = ar + c.bound_r(b) + CULL_SLACK;
             pass = dot3(x, y, z, x, y, z) < rr * rr;
         } else {  // b is a large box: separating-axis bound along its three face normals
             float B[12];
-            c.load<12>(b, lane, B);
+            c.load_u<12>(b, B);
             const float* h = c.rowdata(b) + 12;
             float l[3], e[3];
             to_box_local(B, B + 3, ca, l);
@@ -481,7 +502,7 @@ __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob
 // ------------------------------------------------------------------------------------------
 // configuration batch kernel (A5 / A6 batch variant)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) check_configs_kernel(ConfigParams p) {
+__global__ void __launch_bounds__(THREADS, 5) check_configs_kernel(ConfigParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
     stage_scene(sm, p.blob, p.blob_words, p.n_shapes, p.rule);
@@ -540,7 +561,7 @@ __global__ void __launch_bounds__(THREADS) check_configs_kernel(ConfigParams p) 
 // edge batch kernel (A8 batch variant): one CTA per edge at a time, 32 interpolation points
 // per step in the reference's binary order, early exit on the first colliding step
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) check_edges_kernel(EdgeParams p) {
+__global__ void __launch_bounds__(THREADS, 5) check_edges_kernel(EdgeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
     RobotRule none{};
