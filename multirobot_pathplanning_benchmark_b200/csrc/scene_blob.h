@@ -19,8 +19,8 @@
 #define MRB_SCENE_BLOB_H
 
 #define MRB_BLOB_MAGIC 0x4D524232
-#define MRB_BLOB_VERSION 5
-#define MRB_HDR_WORDS 48
+#define MRB_BLOB_VERSION 6
+#define MRB_HDR_WORDS 112
 #define MRB_FRAME_WORDS 16
 #define MRB_SHAPE_WORDS 20
 #define MRB_NUM_PAIR_TYPES 8
@@ -70,6 +70,16 @@
 #define MRB_H_OFF_PAIRS 20 /* [20..27] */
 #define MRB_H_N_PAIRS 28   /* [28..35] */
 #define MRB_H_OFF_SHAPE_ROBOT 36
+#define MRB_H_OFF_SCENTRE 37 /* static shape centres, 4 floats each */
+/* broadphase sublists [type][sublist] -> (record offset, count).  A record is 2 words
+ * { (byte offset of moving shape X inside a W row) | (Y id << 16), float threshold }; the n records
+ * of a sublist are followed by n packed (a | b << 16) pair ids for the narrowphase.
+ *   sublist 0: Y moving (id = its byte offset), bounding spheres, threshold = (bX + bY + slack)^2
+ *   sublist 1: Y static (id = static index),    bounding spheres, same threshold
+ *   sublist 2: Y a large static box (id = static index), separating-axis bound along the box's
+ *              face normals; threshold = rX + rY + slack (X a segment) or bX + rY + slack */
+#define MRB_H_BP 48
+#define MRB_BP_SUBLISTS 3
 
 /* threshold below which a box-box edge-edge SAT axis (|a_i x b_j|^2) is skipped as degenerate */
 #define MRB_SAT_PARALLEL_EPS2 1e-4

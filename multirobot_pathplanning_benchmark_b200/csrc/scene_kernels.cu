@@ -30,8 +30,7 @@
 namespace mrb {
 
 constexpr int TILE = 32;
-constexpr int WARPS = 4;
-constexpr int THREADS = TILE * WARPS;
+constexpr int MAX_WARPS = 4;  // warps cooperating on one tile of 32 configurations: 2 or 4 (template parameter)
 constexpr unsigned FULL = 0xffffffffu;
 
 struct Smem {
@@ -56,7 +55,7 @@ __host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_w
     off[2] = o; o = align16(o + size_t(TILE) * D * 4);
     off[3] = o; o = align16(o + size_t(world_words) * TILE * 4);
     off[4] = o; o = align16(o + size_t(2) * TILE * 4);
-    off[5] = o; o = align16(o + size_t(WARPS) * 64 * 4);
+    off[5] = o; o = align16(o + size_t(MAX_WARPS) * 64 * 4);
     off[6] = o; o = align16(o + size_t(n_shapes));
     off[7] = o; o = align16(o + 3 * 8);
     off[8] = o; o = align16(o + 40 * 4);
@@ -105,6 +104,7 @@ __device__ __forceinline__ void xform_point(const float* R, const float* t, cons
     for (int r = 0; r < 3; r++) w[r * stride] = fmaf(R[r * 3], l[0], fmaf(R[r * 3 + 1], l[1], fmaf(R[r * 3 + 2], l[2], t[r])));
 }
 
+template <int WARPS>
 __device__ __forceinline__ void fk_phase(const uint32_t* bi, const float* q, float* W, int warp, int lane) {
     const float* bf = reinterpret_cast<const float*>(bi);
     const int n_chains = bi[MRB_H_NCHAINS];
@@ -331,93 +331,142 @@ __device__ __forceinline__ float narrow_pair(const TileCtx& c, int a, int b, int
 }
 
 template <int T>
-__device__ __noinline__ void drain(const TileCtx& c, int off, uint32_t entry, bool valid) {
+__device__ __noinline__ void drain(const TileCtx& c, int off_ids, uint32_t entry, bool valid) {
     if (valid) {
         const int cfg = entry & 31;
-        const uint32_t pk = c.bi[off + (entry >> 5)];
+        const uint32_t pk = c.bi[off_ids + (entry >> 5)];
         const int a = pk & 0xffff, b = (pk >> 16) & 0xfff;
         c.add_pen(cfg, a, b, narrow_pair<T>(c, a, b, cfg));
     }
 }
 
-template <int T>
-__device__ __forceinline__ void run_type(const TileCtx& c, int warp, bool skip_decided, unsigned tol_fx) {
-    constexpr int coreA = (T == MRB_PT_SEG_SEG || T == MRB_PT_SEG_BOX) ? MRB_CORE_SEG
-                          : (T == MRB_PT_BOX_BOX || T == MRB_PT_BOX_CYLZ) ? MRB_CORE_BOX
-                                                                         : MRB_CORE_POINT;
-    constexpr int coreB = (T == MRB_PT_SEG_SEG || T == MRB_PT_POINT_SEG) ? MRB_CORE_SEG
-                          : (T == MRB_PT_SEG_BOX || T == MRB_PT_POINT_BOX || T == MRB_PT_BOX_BOX) ? MRB_CORE_BOX
-                                                                                                   : MRB_CORE_POINT;
-    const uint32_t* bi = c.bi;
-    const int n = bi[MRB_H_N_PAIRS + T], off = bi[MRB_H_OFF_PAIRS + T];
-    if (n == 0) return;
-    const int lo = (n * warp) / WARPS, hi = (n * (warp + 1)) / WARPS;
-    const int lane = c.lane;
-    const unsigned lt = (1u << lane) - 1u;
-    int qn = 0, prev_a = -1;
-    float ca[3] = {0.f, 0.f, 0.f}, ha[3] = {0.f, 0.f, 0.f}, ar = 0.f, ra = 0.f;
-    bool decided = false;
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t pk = bi[off + i];
-        const int a = pk & 0xffff, b = (pk >> 16) & 0xfff, kind = pk >> 28;
-        if (a != prev_a) {  // warp-uniform
-            load_centre_u<coreA, true>(c, a, ca, ha);
-            ar = c.bound_r(a);
-            ra = c.radius(a);
-            prev_a = a;
-            if (skip_decided) decided = c.pen_fx[lane] > tol_fx;
-        }
-        bool pass;
-        if (kind == 0) {  // bounding spheres
-            float cb[3], hb[3];
-            load_centre_u<coreB, false>(c, b, cb, hb);
-            const float x = ca[0] - cb[0], y = ca[1] - cb[1], z = ca[2] - cb[2];
-            const float rr = ar + c.bound_r(b) + CULL_SLACK;
-            pass = dot3(x, y, z, x, y, z) < rr * rr;
-        } else {  // b is a large box: separating-axis bound along its three face normals
-            float B[12];
-            c.load_u<12>(b, B);
-            const float* h = c.rowdata(b) + 12;
-            float l[3], e[3];
-            to_box_local(B, B + 3, ca, l);
-            float lb;
-            if (kind == 2) {
-                const float* R = B + 3;
-                e[0] = fabsf(dot3(R[0], R[3], R[6], ha[0], ha[1], ha[2]));
-                e[1] = fabsf(dot3(R[1], R[4], R[7], ha[0], ha[1], ha[2]));
-                e[2] = fabsf(dot3(R[2], R[5], R[8], ha[0], ha[1], ha[2]));
-                lb = fmaxf(fmaxf(fabsf(l[0]) - e[0] - h[0], fabsf(l[1]) - e[1] - h[1]), fabsf(l[2]) - e[2] - h[2]) - ra;
-            } else {
-                lb = fmaxf(fmaxf(fabsf(l[0]) - h[0], fabsf(l[1]) - h[1]), fabsf(l[2]) - h[2]) - ar;
+__device__ __noinline__ void drain_any(const TileCtx& c, int type, int off_ids, uint32_t entry, bool valid) {
+    switch (type) {  // warp-uniform
+        case MRB_PT_SEG_SEG: drain<MRB_PT_SEG_SEG>(c, off_ids, entry, valid); break;
+        case MRB_PT_SEG_BOX: drain<MRB_PT_SEG_BOX>(c, off_ids, entry, valid); break;
+        case MRB_PT_POINT_POINT: drain<MRB_PT_POINT_POINT>(c, off_ids, entry, valid); break;
+        case MRB_PT_POINT_SEG: drain<MRB_PT_POINT_SEG>(c, off_ids, entry, valid); break;
+        case MRB_PT_POINT_BOX: drain<MRB_PT_POINT_BOX>(c, off_ids, entry, valid); break;
+        default: drain<MRB_PT_BOX_BOX>(c, off_ids, entry, valid); break;
+    }
+}
+
+// Per-warp survivor queue.  The broadphase marks, per lane (= configuration), which of the last
+// <= 32 records passed in a bit mask; flush() turns the masks into queue entries, one round
+// per set bit, and drains 32 entries at a time through the exact narrowphase.
+struct Survivors {
+    const TileCtx& c;
+    int type, off_ids, qn;
+    __device__ __forceinline__ void flush(uint32_t mask, int first_record) {
+        const unsigned lt = (1u << c.lane) - 1u;
+        for (;;) {
+            const unsigned m = __ballot_sync(FULL, mask != 0u);
+            if (!m) break;
+            if (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                c.queue[qn + __popc(m & lt)] = ((uint32_t)(first_record + j) << 5) | (uint32_t)c.lane;
             }
-            pass = lb - c.radius(b) < CULL_SLACK;
-        }
-        pass = pass && !decided;
-        const unsigned m = __ballot_sync(FULL, pass);
-        if (m) {
-            if (pass) c.queue[qn + __popc(m & lt)] = ((uint32_t)i << 5) | (uint32_t)lane;
             qn += __popc(m);
             __syncwarp();
             if (qn >= TILE) {
-                const uint32_t entry = c.queue[lane];
-                const uint32_t tail = c.queue[TILE + lane];
+                const uint32_t entry = c.queue[c.lane];
+                const uint32_t tail = c.queue[TILE + c.lane];
                 __syncwarp();
                 qn -= TILE;
-                if (lane < qn) c.queue[lane] = tail;
+                if (c.lane < qn) c.queue[c.lane] = tail;
                 __syncwarp();
-                drain<T>(c, off, entry, true);
+                drain_any(c, type, off_ids, entry, true);
             }
         }
     }
-    if (qn > 0) {
-        const uint32_t entry = c.queue[lane];
-        drain<T>(c, off, entry, lane < qn);
+    __device__ __forceinline__ void finish() {
+        if (qn > 0) {
+            const uint32_t entry = c.queue[c.lane];
+            drain_any(c, type, off_ids, entry, c.lane < qn);
+        }
+        qn = 0;
+        __syncwarp();
     }
-    __syncwarp();
+};
+
+// One routine for every queued pair type: the broadphase only needs the records.
+template <int WARPS>
+__device__ __noinline__ void run_queued_types(const TileCtx& c, int warp, bool skip_decided, unsigned tol_fx) {
+    const uint32_t* bi = c.bi;
+    const float* bf = c.bf;
+    const int lane = c.lane;
+    const char* Wl = reinterpret_cast<const char*>(c.W + lane);  // this lane's column of W
+    const float4* scentre = reinterpret_cast<const float4*>(bf + bi[MRB_H_OFF_SCENTRE]);
+    for (int type = 0; type <= MRB_PT_BOX_BOX; ++type) {
+        for (int sub = 0; sub < MRB_BP_SUBLISTS; ++sub) {
+            const int n = bi[MRB_H_BP + (type * MRB_BP_SUBLISTS + sub) * 2 + 1];
+            if (n == 0) continue;
+            const int off = bi[MRB_H_BP + (type * MRB_BP_SUBLISTS + sub) * 2];
+            const int lo = (n * warp) / WARPS, hi = (n * (warp + 1)) / WARPS;
+            Survivors sv{c, type, off + 2 * n, 0};
+            const uint2* rec = reinterpret_cast<const uint2*>(bi + off);
+            const bool seg_x = type == MRB_PT_SEG_BOX;
+            unsigned prev_x = 0xffffffffu;
+            float cx = 0.f, cy = 0.f, cz = 0.f, hx = 0.f, hy = 0.f, hz = 0.f;
+            for (int base = lo; base < hi; base += 32) {
+                const int cnt = min(32, hi - base);
+                uint32_t mask = 0u;
+                if (sub == 0) {  // partner moving: bounding spheres
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint2 r = rec[base + j];
+                        const unsigned xo = r.x & 0xffffu;
+                        if (xo != prev_x) {  // warp-uniform: records are sorted by X
+                            const float* px = reinterpret_cast<const float*>(Wl + xo);
+                            cx = px[0]; cy = px[TILE]; cz = px[2 * TILE];
+                            prev_x = xo;
+                        }
+                        const float* py = reinterpret_cast<const float*>(Wl + (r.x >> 16));
+                        const float x = cx - py[0], y = cy - py[TILE], z = cz - py[2 * TILE];
+                        mask |= (dot3(x, y, z, x, y, z) < __uint_as_float(r.y) ? 1u : 0u) << j;
+                    }
+                } else if (sub == 1) {  // partner static: bounding spheres
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint2 r = rec[base + j];
+                        const unsigned xo = r.x & 0xffffu;
+                        if (xo != prev_x) {
+                            const float* px = reinterpret_cast<const float*>(Wl + xo);
+                            cx = px[0]; cy = px[TILE]; cz = px[2 * TILE];
+                            prev_x = xo;
+                        }
+                        const float4 cb = scentre[r.x >> 16];
+                        const float x = cx - cb.x, y = cy - cb.y, z = cz - cb.z;
+                        mask |= (dot3(x, y, z, x, y, z) < __uint_as_float(r.y) ? 1u : 0u) << j;
+                    }
+                } else {  // partner is a large static box: separating-axis bound along its face normals
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint2 r = rec[base + j];
+                        const unsigned xo = r.x & 0xffffu;
+                        if (xo != prev_x) {
+                            const float* px = reinterpret_cast<const float*>(Wl + xo);
+                            cx = px[0]; cy = px[TILE]; cz = px[2 * TILE];
+                            if (seg_x) { hx = px[3 * TILE]; hy = px[4 * TILE]; hz = px[5 * TILE]; }
+                            prev_x = xo;
+                        }
+                        const float* B = bf + c.row(c.nmov + (r.x >> 16)) + 4;  // c[3], R[9], half[3]
+                        const float* R = B + 3;
+                        const float x = cx - B[0], y = cy - B[1], z = cz - B[2];
+                        const float l0 = fabsf(dot3(R[0], R[3], R[6], x, y, z)) - B[12] - fabsf(dot3(R[0], R[3], R[6], hx, hy, hz));
+                        const float l1 = fabsf(dot3(R[1], R[4], R[7], x, y, z)) - B[13] - fabsf(dot3(R[1], R[4], R[7], hx, hy, hz));
+                        const float l2 = fabsf(dot3(R[2], R[5], R[8], x, y, z)) - B[14] - fabsf(dot3(R[2], R[5], R[8], hx, hy, hz));
+                        mask |= (fmaxf(fmaxf(l0, l1), l2) < __uint_as_float(r.y) ? 1u : 0u) << j;
+                    }
+                }
+                if (skip_decided && c.pen_fx[lane] > tol_fx) mask = 0u;
+                sv.flush(mask, base);
+            }
+            sv.finish();
+        }
+    }
 }
 
 // cheap planar pair types are evaluated directly (no queue): lane = configuration
-template <int T>
+template <int T, int WARPS>
 __device__ __forceinline__ void run_type_direct(const TileCtx& c, int warp) {
     const uint32_t* bi = c.bi;
     const int n = bi[MRB_H_N_PAIRS + T], off = bi[MRB_H_OFF_PAIRS + T];
@@ -442,6 +491,7 @@ __device__ __forceinline__ void run_type_direct(const TileCtx& c, int warp) {
 
 // All THREADS threads call this.  On return warp 0 holds, per lane, the configuration's total
 // penetration (return value) and whether a relevant pair penetrates (*relpen_out).
+template <int WARPS>
 __device__ __forceinline__ float process_tile(const Smem& sm, const float* q_tile, int D, float tol, bool early, bool rule,
                                               bool* relpen_out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -451,7 +501,7 @@ __device__ __forceinline__ float process_tile(const Smem& sm, const float* q_til
         sm.pen_fx[lane] = 0u;
         sm.relf[lane] = 0u;
     }
-    fk_phase(bi, q_tile + lane * D, sm.W, warp, lane);
+    fk_phase<WARPS>(bi, q_tile + lane * D, sm.W, warp, lane);
     __syncthreads();
 
     const TileCtx ctx{bi, reinterpret_cast<const float*>(bi), sm.W, sm.sflag, sm.pen_fx, sm.relf, sm.queue + warp * QCAP,
@@ -459,14 +509,9 @@ __device__ __forceinline__ float process_tile(const Smem& sm, const float* q_til
     // a configuration is decided once its accumulated penetration exceeds tol - static part
     const float budget = fmaxf(tol - static_pen, 0.f);
     const unsigned tol_fx = (unsigned)fminf(budget * PEN_SCALE, 4.0e9f);
-    run_type<MRB_PT_SEG_SEG>(ctx, warp, early, tol_fx);
-    run_type<MRB_PT_SEG_BOX>(ctx, warp, early, tol_fx);
-    run_type<MRB_PT_POINT_POINT>(ctx, warp, early, tol_fx);
-    run_type<MRB_PT_POINT_SEG>(ctx, warp, early, tol_fx);
-    run_type<MRB_PT_POINT_BOX>(ctx, warp, early, tol_fx);
-    run_type<MRB_PT_BOX_BOX>(ctx, warp, early, tol_fx);
-    run_type_direct<MRB_PT_CYLZ_CYLZ>(ctx, warp);
-    run_type_direct<MRB_PT_BOX_CYLZ>(ctx, warp);
+    run_queued_types<WARPS>(ctx, warp, early, tol_fx);
+    run_type_direct<MRB_PT_CYLZ_CYLZ, WARPS>(ctx, warp);
+    run_type_direct<MRB_PT_BOX_CYLZ, WARPS>(ctx, warp);
     __syncthreads();
     float total = 0.f;
     if (warp == 0) {
@@ -478,7 +523,7 @@ __device__ __forceinline__ float process_tile(const Smem& sm, const float* q_til
 
 // common prologue: barriers, blob staging through TMA, A6 shape flags
 __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob, int blob_words, int n_shapes,
-                                            const RobotRule& rr) {
+                                            const RobotRule& rr, int THREADS) {
     if (threadIdx.x == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
@@ -502,10 +547,12 @@ __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob
 // ------------------------------------------------------------------------------------------
 // configuration batch kernel (A5 / A6 batch variant)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 5) check_configs_kernel(ConfigParams p) {
+template <int WARPS>
+__global__ void __launch_bounds__(TILE * WARPS, 20 / WARPS) check_configs_kernel(ConfigParams p) {
+    constexpr int THREADS = TILE * WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
-    stage_scene(sm, p.blob, p.blob_words, p.n_shapes, p.rule);
+    stage_scene(sm, p.blob, p.blob_words, p.n_shapes, p.rule, THREADS);
 
     const int D = p.D;
     const float tol = p.tol < 0.f ? reinterpret_cast<const float*>(sm.blob)[MRB_H_TOL] : p.tol;
@@ -547,7 +594,7 @@ __global__ void __launch_bounds__(THREADS, 5) check_configs_kernel(ConfigParams 
             __syncthreads();
         }
         bool relpen = false;
-        const float total = process_tile(sm, sm.q[buf], D, tol, early, p.rule.enabled, &relpen);
+        const float total = process_tile<WARPS>(sm, sm.q[buf], D, tol, early, p.rule.enabled, &relpen);
         if (warp == 0 && lane < nvalid) {
             const bool coll = p.rule.enabled ? (total > tol && relpen) : (total > tol);
             p.flags[first + lane] = coll ? 0 : 1;
@@ -561,11 +608,13 @@ __global__ void __launch_bounds__(THREADS, 5) check_configs_kernel(ConfigParams 
 // edge batch kernel (A8 batch variant): one CTA per edge at a time, 32 interpolation points
 // per step in the reference's binary order, early exit on the first colliding step
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 5) check_edges_kernel(EdgeParams p) {
+template <int WARPS>
+__global__ void __launch_bounds__(TILE * WARPS, 20 / WARPS) check_edges_kernel(EdgeParams p) {
+    constexpr int THREADS = TILE * WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
     RobotRule none{};
-    stage_scene(sm, p.blob, p.blob_words, p.n_shapes, none);
+    stage_scene(sm, p.blob, p.blob_words, p.n_shapes, none, THREADS);
 
     const int D = p.D;
     const float tol = p.tol < 0.f ? reinterpret_cast<const float*>(sm.blob)[MRB_H_TOL] : p.tol;
@@ -618,7 +667,7 @@ __global__ void __launch_bounds__(THREADS, 5) check_edges_kernel(EdgeParams p) {
             }
             __syncthreads();
             bool relpen;
-            const float total = process_tile(sm, sm.q[0], D, tol, false, false, &relpen);
+            const float total = process_tile<WARPS>(sm, sm.q[0], D, tol, false, false, &relpen);
             if (warp == 0) {
                 const unsigned hit = __ballot_sync(FULL, s_idx[lane] >= 0 && total > tol);
                 if (lane == 0 && hit) s_edge[2] = base + __ffs(hit) - 1;
@@ -679,14 +728,18 @@ static int num_sms() {
 }
 
 template <typename K>
-static int grid_for(K kernel, size_t smem, int* blocks_per_sm) {
+static int grid_for(K kernel, int threads, size_t smem) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
     if (occ < 1) occ = 1;
-    *blocks_per_sm = occ;
     return occ * num_sms();
 }
+
+// warps per tile: small scenes run two warps per tile (balanced FK for two-robot scenes, cheap
+// barriers); scenes with a large per-configuration footprint share a tile among four warps to
+// keep enough warps resident
+static int warps_per_tile(int world_words) { return world_words >= 128 ? 4 : 2; }
 
 cudaError_t launch_static_penetration(uint32_t* blob, cudaStream_t st) {
     static_penetration_kernel<<<1, 32, 0, st>>>(blob);
@@ -696,23 +749,33 @@ cudaError_t launch_static_penetration(uint32_t* blob, cudaStream_t st) {
 cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
     const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes);
-    int occ;
-    int grid = grid_for(check_configs_kernel, smem, &occ);
     const int64_t n_tiles = (p.B + TILE - 1) / TILE;
-    if (grid > n_tiles) grid = (int)n_tiles;
-    check_configs_kernel<<<grid, THREADS, smem, st>>>(p);
+    if (warps_per_tile(p.world_words) == 4) {
+        int grid = grid_for(check_configs_kernel<4>, 128, smem);
+        if (grid > n_tiles) grid = (int)n_tiles;
+        check_configs_kernel<4><<<grid, 128, smem, st>>>(p);
+    } else {
+        int grid = grid_for(check_configs_kernel<2>, 64, smem);
+        if (grid > n_tiles) grid = (int)n_tiles;
+        check_configs_kernel<2><<<grid, 64, smem, st>>>(p);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t launch_check_edges(const EdgeParams& p, cudaStream_t st) {
     if (p.E <= 0) return cudaSuccess;
     const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes);
-    int occ;
-    int grid = grid_for(check_edges_kernel, smem, &occ);
-    if (grid > p.E) grid = (int)p.E;
     cudaError_t err = cudaMemsetAsync(p.counter, 0, sizeof(int), st);
     if (err != cudaSuccess) return err;
-    check_edges_kernel<<<grid, THREADS, smem, st>>>(p);
+    if (warps_per_tile(p.world_words) == 4) {
+        int grid = grid_for(check_edges_kernel<4>, 128, smem);
+        if (grid > p.E) grid = (int)p.E;
+        check_edges_kernel<4><<<grid, 128, smem, st>>>(p);
+    } else {
+        int grid = grid_for(check_edges_kernel<2>, 64, smem);
+        if (grid > p.E) grid = (int)p.E;
+        check_edges_kernel<2><<<grid, 64, smem, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

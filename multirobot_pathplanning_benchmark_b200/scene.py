@@ -372,8 +372,8 @@ class Scene:
 # blob layout (mirror of csrc/scene_blob.h)
 # ----------------------------------------------------------------------------------
 BLOB_MAGIC = 0x4D524232
-BLOB_VERSION = 5
-HDR_WORDS = 48
+BLOB_VERSION = 6
+HDR_WORDS = 112
 FRAME_WORDS = 16
 SHAPE_WORDS = 20
 LARGE_BOX_BOUND = 0.3  # boxes with a bounding radius above this use the face-normal broadphase bound
@@ -387,7 +387,12 @@ H_OFF_FRAMES, H_OFF_SHAPES, H_OFF_CHAINS, H_OFF_STATIC_PAIRS, H_N_STATIC_PAIRS =
 H_TOL, H_STATIC_PEN, H_TOTAL_WORDS, H_NROBOTS = 13, 14, 15, 16
 H_OFF_PAIRS = 20   # [20..27]
 H_N_PAIRS = 28     # [28..35]
-H_OFF_SHAPE_ROBOT = 36  # per-shape robot id (moving shapes: owning robot; static: -1; held: holder)
+H_OFF_SHAPE_ROBOT = 36
+H_OFF_SCENTRE = 37   # static shape centres, 4 floats each
+H_BP = 48            # broadphase sublists: [type][sublist] -> (record offset, count), 8 x 3 x 2 words
+BP_SUBLISTS = 3      # 0: partner moving (bounding spheres), 1: partner static (bounding spheres),
+                     # 2: partner is a large static box (face-normal separating-axis bound)
+CULL_SLACK = 1e-3    # broadphase keeps everything closer than 1 mm  # per-shape robot id (moving shapes: owning robot; static: -1; held: holder)
 
 
 @dataclass
@@ -550,6 +555,33 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
     for t in range(NUM_PAIR_TYPES):
         typed[t].sort()
 
+    # --- broadphase records: per type three sublists of (X = a moving shape, Y = its partner) ---
+    # record = 2 words: (byte offset of X in a W row) | (Y id << 16), float threshold
+    #   sublist 0: Y moving, id = byte offset of Y;      thr = (bound_X + bound_Y + slack)^2
+    #   sublist 1: Y static, id = static shape index;    thr = (bound_X + bound_Y + slack)^2
+    #   sublist 2: Y large static box, id = static index; thr = r_X + r_Y + slack (X a segment: bound on
+    #              its core along the box face normals) or bound_X + r_Y + slack (otherwise)
+    # each record is followed (in a parallel array) by the pair's packed shape ids for the narrowphase
+    def wbytes(i):
+        assert 0 <= shape_rows[i][2] * 128 < 65536, "world data of a configuration exceeds 64 KB"
+        return shape_rows[i][2] * 128
+
+    bp: List[List[List[Tuple[int, float, int]]]] = [[[] for _ in range(BP_SUBLISTS)] for _ in range(NUM_PAIR_TYPES)]
+    for t in range(NUM_PAIR_TYPES):
+        for (ia, ib, kind) in typed[t]:
+            x, y = (ia, ib) if ia < n_mov else (ib, ia)   # X is always a moving shape
+            packed = ia | (ib << 16)
+            rx, ry = shape_rows[x][3], shape_rows[y][3]
+            if y < n_mov:
+                bp[t][0].append((wbytes(x) | (wbytes(y) << 16), (bound_rs[x] + bound_rs[y] + CULL_SLACK) ** 2, packed))
+            elif kind and y == ib:
+                thr = (rx + ry if shape_rows[x][0] == CORE_SEG else bound_rs[x] + ry) + CULL_SLACK
+                bp[t][2].append((wbytes(x) | ((y - n_mov) << 16), thr, packed))
+            else:
+                bp[t][1].append((wbytes(x) | ((y - n_mov) << 16), (bound_rs[x] + bound_rs[y] + CULL_SLACK) ** 2, packed))
+        for sl in bp[t]:
+            sl.sort(key=lambda r: (r[0] & 0xffff, r[0] >> 16))
+
     # --- assemble words ---
     n_shapes = len(shapes)
     off = HDR_WORDS
@@ -567,6 +599,15 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
     off += 3 * len(static_pairs)
     off_shape_robot = off
     off += n_shapes
+    off = (off + 3) // 4 * 4
+    off_scentre = off
+    off += 4 * n_sta
+    off_bp = [[0] * BP_SUBLISTS for _ in range(NUM_PAIR_TYPES)]
+    for t in range(NUM_PAIR_TYPES):
+        for k in range(BP_SUBLISTS):
+            off = (off + 1) // 2 * 2          # records are read as 8-byte words
+            off_bp[t][k] = off
+            off += 3 * len(bp[t][k])          # n records (2 words) then n packed pair ids
     total = (off + 3) // 4 * 4   # 16-byte multiple for cp.async.bulk
 
     ints = np.zeros(total, np.int64)
@@ -607,6 +648,20 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
     for t in range(NUM_PAIR_TYPES):
         for i, (a, b_, kind) in enumerate(typed[t]):
             seti(off_pairs[t] + i, a | (b_ << 16) | (kind << 28))
+    seti(H_OFF_SCENTRE, off_scentre)
+    for i in range(n_sta):
+        core, _, _, _, data, _ = shape_rows[n_mov + i]
+        ctr = [0.5 * (data[k] + data[3 + k]) for k in range(3)] if core == CORE_SEG else data[:3]
+        for k in range(3):
+            setf(off_scentre + 4 * i + k, ctr[k])
+        setf(off_scentre + 4 * i + 3, 0.0)
+    for t in range(NUM_PAIR_TYPES):
+        for k in range(BP_SUBLISTS):
+            n = len(bp[t][k])
+            seti(H_BP + (t * BP_SUBLISTS + k) * 2, off_bp[t][k]), seti(H_BP + (t * BP_SUBLISTS + k) * 2 + 1, n)
+            for i, (ids, thr, packed) in enumerate(bp[t][k]):
+                seti(off_bp[t][k] + 2 * i, ids), setf(off_bp[t][k] + 2 * i + 1, thr)
+                seti(off_bp[t][k] + 2 * n + i, packed)
     for i, (t, a, b_) in enumerate(static_pairs):
         seti(off_static + 3 * i, t), seti(off_static + 3 * i + 1, a), seti(off_static + 3 * i + 2, b_)
 
