@@ -92,6 +92,43 @@ int mrb200_check_edges(const mrb200_scene_t* scene, int slot, const float* q1_de
 /* introspection of a slot: D, n_shapes, n_pairs (dynamic), shared memory bytes per CTA */
 int mrb200_scene_info(const mrb200_scene_t* scene, int slot, int32_t* out4);
 
+/* ---- distances and neighbour search: batch_config_dist (P/problems/core/configuration.py:303-349),
+ * PRM get_neighbors (P/planners/prm/prm_graph.py:389-549), RRT* near (P/planners/rrtstar_base.py:
+ * 439-453, 1296-1337), IT* get_neighbors (P/planners/itstar_base.py:1388-1527) ----
+ * All coordinates are fp64 like the reference's arrays.  slices_host: R x [start, end) per robot.
+ * metric: 0 euclidean, 1 sum_euclidean, 2 max_euclidean, 3 max (infinity norm). */
+#define MRB200_METRIC_EUCLIDEAN 0
+#define MRB200_METRIC_SUM_EUCLIDEAN 1
+#define MRB200_METRIC_MAX_EUCLIDEAN 2
+#define MRB200_METRIC_MAX 3
+/* one-to-many distance: out[n] = dist(q, pts[n]) */
+int mrb200_batch_dist(const double* q_dev /*[D]*/, const double* pts_dev /*[N, D]*/, int64_t N, int D,
+                      const int32_t* slices_host, int R, int metric, double* out_dev /*[N]*/,
+                      mrb200_stream_t stream);
+/* k nearest neighbours of every query row, ascending (distance, index); rows with fewer than k
+ * corpus points are padded with index -1 / distance +inf.  out_dist_dev nullable.  The workspace
+ * (device, mrb200_knn_workspace_bytes) is scratch for partial results.
+ * mode: 0 = automatic, 1 = exact fp64 CUDA-core path, 2 = tensor-core candidates + fp64 re-rank
+ * (euclidean / max_euclidean only); both return the same indices. */
+size_t mrb200_knn_workspace_bytes(int64_t Q, int64_t N, int D, int k);
+int mrb200_knn(const double* queries_dev /*[Q, D]*/, const double* corpus_dev /*[N, D]*/, int64_t Q, int64_t N,
+               int D, const int32_t* slices_host, int R, int metric, int k, int32_t* out_idx_dev /*[Q, k]*/,
+               double* out_dist_dev /*[Q, k]*/, void* workspace_dev, size_t workspace_bytes, int mode,
+               mrb200_stream_t stream);
+/* radius search in two launches around a caller-side exclusive scan.  splits =
+ * mrb200_radius_splits(Q, N) corpus ranges are searched independently; counts_dev is [Q * splits]
+ * (row major).  radii_dev (per query) nullable, then `radius` applies to all.  inclusive = 0:
+ * d < r (PRM); 1: d <= r + 1e-10 (RRT* / IT*).  fill writes the neighbour indices of row i, in
+ * ascending index order, starting at offsets_dev[i * splits] (offsets = exclusive scan of counts). */
+int mrb200_radius_splits(int64_t Q, int64_t N);
+int mrb200_radius_count(const double* queries_dev, const double* corpus_dev, int64_t Q, int64_t N, int D,
+                        const int32_t* slices_host, int R, int metric, const double* radii_dev, double radius,
+                        int inclusive, int splits, int64_t* counts_dev, mrb200_stream_t stream);
+int mrb200_radius_fill(const double* queries_dev, const double* corpus_dev, int64_t Q, int64_t N, int D,
+                       const int32_t* slices_host, int R, int metric, const double* radii_dev, double radius,
+                       int inclusive, int splits, const int64_t* offsets_dev, int32_t* out_idx_dev,
+                       double* out_dist_dev, mrb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

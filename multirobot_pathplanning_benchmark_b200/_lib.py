@@ -35,6 +35,15 @@ SIGNATURES = {
     "mrb200_check_edges": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int32,
                                      C.c_int, C.c_float, c_vp, c_vp, c_vp]),
     "mrb200_scene_info": (C.c_int, [c_vp, C.c_int, c_i32p]),
+    "mrb200_batch_dist": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, c_vp, c_vp]),
+    "mrb200_knn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "mrb200_knn": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp,
+                             C.c_size_t, C.c_int, c_vp]),
+    "mrb200_radius_splits": (C.c_int, [C.c_int64, C.c_int64]),
+    "mrb200_radius_count": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, c_vp, C.c_double,
+                                      C.c_int, C.c_int, c_vp, c_vp]),
+    "mrb200_radius_fill": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, c_vp, C.c_double,
+                                     C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
 }
 
 

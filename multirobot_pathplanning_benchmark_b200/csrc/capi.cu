@@ -10,6 +10,7 @@
 
 #include "../../include/mrb200.h"
 #include "kernels.h"
+#include "knn_common.cuh"
 #include "scene_blob.h"
 
 namespace {
@@ -280,6 +281,92 @@ int mrb200_check_edges(const mrb200_scene_t* sc, int slot, const float* q1, cons
     if (e != cudaSuccess) return cuda_fail(e, "check_edges");
     g_launches++;
     return MRB200_OK;
+}
+
+// ------------------------------------------------------------------ distances / neighbours
+static int make_slices(const int32_t* slices_host, int R, int D, int metric, mrb::Slices* out) {
+    if (D < 1 || D > mrb::KNN_MAX_D) return fail(MRB200_ERR_ARG, "D must be in [1, %d]", mrb::KNN_MAX_D);
+    if (metric < 0 || metric > 3) return fail(MRB200_ERR_ARG, "unknown metric %d", metric);
+    memset(out, 0, sizeof(*out));
+    if (metric == MRB200_METRIC_SUM_EUCLIDEAN || metric == MRB200_METRIC_MAX_EUCLIDEAN) {
+        if (!slices_host || R < 1 || R > mrb::KNN_MAX_R) return fail(MRB200_ERR_ARG, "need 1..%d robot slices", mrb::KNN_MAX_R);
+        out->R = R;
+        for (int r = 0; r < R; r++) {
+            out->start[r] = slices_host[2 * r];
+            out->end[r] = slices_host[2 * r + 1];
+            if (out->start[r] < 0 || out->end[r] > D || out->start[r] >= out->end[r]) return fail(MRB200_ERR_ARG, "bad slice %d", r);
+        }
+    }
+    return MRB200_OK;
+}
+
+int mrb200_batch_dist(const double* q, const double* pts, int64_t N, int D, const int32_t* slices_host, int R, int metric,
+                      double* out_dev, mrb200_stream_t stream) {
+    mrb::Slices sl;
+    if (int rc = make_slices(slices_host, R, D, metric, &sl)) return rc;
+    if (N < 0 || (N && (!q || !pts || !out_dev))) return fail(MRB200_ERR_ARG, "batch_dist: bad argument");
+    if (N == 0) return MRB200_OK;
+    cudaError_t e = mrb::launch_batch_dist(q, pts, N, D, sl, metric, out_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "batch_dist");
+    g_launches++;
+    return MRB200_OK;
+}
+
+size_t mrb200_knn_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
+    if (Q <= 0 || k <= 0) return 16;
+    const int splits = mrb::knn_pick_splits(Q, N);
+    return (size_t)splits * (size_t)Q * (size_t)k * 12 + 256;
+}
+
+int mrb200_knn(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const int32_t* slices_host, int R, int metric,
+               int k, int32_t* out_idx, double* out_dist, void* workspace, size_t workspace_bytes, int mode, mrb200_stream_t stream) {
+    mrb::Slices sl;
+    if (int rc = make_slices(slices_host, R, D, metric, &sl)) return rc;
+    if (Q < 0 || N < 0 || k < 1 || k > 128 || (Q && (!queries || !out_idx)) || (N && !corpus))
+        return fail(MRB200_ERR_ARG, "knn: bad argument (k must be in [1, 128])");
+    if (Q == 0) return MRB200_OK;
+    if (workspace_bytes < mrb200_knn_workspace_bytes(Q, N, D, k) || !workspace) return fail(MRB200_ERR_ARG, "knn: workspace too small");
+    if (mode == 2) return fail(MRB200_ERR_ARG, "knn: tensor-core path not available for this metric / build");
+    const int splits = mrb::knn_pick_splits(Q, N);
+    double* part_d = (double*)workspace;
+    int* part_i = (int*)(part_d + (size_t)splits * Q * k);
+    cudaError_t e = mrb::launch_knn_exact(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, out_idx, out_dist,
+                                          (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "knn");
+    g_launches += 2;
+    return MRB200_OK;
+}
+
+int mrb200_radius_splits(int64_t Q, int64_t N) { return mrb::knn_pick_splits(Q, N); }
+
+static int radius_impl(bool fill, const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const int32_t* slices_host,
+                       int R, int metric, const double* radii, double radius, int inclusive, int splits, int64_t* counts,
+                       const int64_t* offsets, int32_t* out_idx, double* out_dist, mrb200_stream_t stream) {
+    mrb::Slices sl;
+    if (int rc = make_slices(slices_host, R, D, metric, &sl)) return rc;
+    if (Q < 0 || N < 0 || splits < 1 || (Q && !queries) || (N && !corpus) || (Q && !fill && !counts) || (Q && fill && !offsets))
+        return fail(MRB200_ERR_ARG, "radius: bad argument");
+    if (Q == 0) return MRB200_OK;
+    cudaError_t e = mrb::launch_radius(fill, queries, corpus, Q, N, D, sl, metric, radii, radius, inclusive, splits, counts, offsets,
+                                       out_idx, out_dist, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "radius");
+    g_launches++;
+    return MRB200_OK;
+}
+
+int mrb200_radius_count(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const int32_t* slices_host, int R,
+                        int metric, const double* radii, double radius, int inclusive, int splits, int64_t* counts,
+                        mrb200_stream_t stream) {
+    return radius_impl(false, queries, corpus, Q, N, D, slices_host, R, metric, radii, radius, inclusive, splits, counts, nullptr,
+                       nullptr, nullptr, stream);
+}
+
+int mrb200_radius_fill(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const int32_t* slices_host, int R,
+                       int metric, const double* radii, double radius, int inclusive, int splits, const int64_t* offsets,
+                       int32_t* out_idx, double* out_dist, mrb200_stream_t stream) {
+    if (Q > 0 && !out_idx) return fail(MRB200_ERR_ARG, "radius_fill: out_idx is null");
+    return radius_impl(true, queries, corpus, Q, N, D, slices_host, R, metric, radii, radius, inclusive, splits, nullptr, offsets,
+                       out_idx, out_dist, stream);
 }
 
 }  // extern "C"

@@ -63,6 +63,17 @@ cudaError_t launch_abstract_edges(const AbstractSceneData& sc, const double* q1,
                                   double resolution, const int32_t* N, int n_start, int n_max, int include_endpoints,
                                   uint8_t* flags, int32_t* first_pos, int* counter, cudaStream_t st);
 
+// ---- distances and neighbour search (knn_kernels.cu) ----
+struct Slices;
+int knn_pick_splits(int64_t Q, int64_t N);
+cudaError_t launch_batch_dist(const double* q, const double* pts, int64_t N, int D, const Slices& sl, int metric, double* out,
+                              cudaStream_t st);
+cudaError_t launch_knn_exact(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
+                             int k, int splits, double* part_d, int* part_i, int32_t* out_idx, double* out_dist, cudaStream_t st);
+cudaError_t launch_radius(bool fill, const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl,
+                          int metric, const double* radii, double radius, int inclusive, int splits, int64_t* counts,
+                          const int64_t* offsets, int32_t* out_idx, double* out_dist, cudaStream_t st);
+
 // out: device [n_threads] floats; call with out == nullptr to query n_threads
 cudaError_t launch_fp32_probe(int iters, float* out, int* n_threads, cudaStream_t st);
 

@@ -1,0 +1,128 @@
+"""Distance metrics and neighbour search on the device (tensor in / tensor out).
+
+Reference calls replaced (P/ = src/multi_robot_multi_goal_planning/ in the reference):
+  batch_config_dist                 P/problems/core/configuration.py:342-349 (impl :303-329)
+  PRM get_neighbors k-NN / r-disc   P/planners/prm/prm_graph.py:389-549
+  RRT* nearest / near               P/planners/rrtstar_base.py:439-453, 1228-1337
+  IT* get_neighbors                 P/planners/itstar_base.py:1388-1527
+Coordinates are fp64 like the reference's arrays; returned neighbour indices are int32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+METRICS = {"euclidean": 0, "sum_euclidean": 1, "max_euclidean": 2, "max": 3}
+
+
+def _slices(slices) -> Tuple[Optional[np.ndarray], int]:
+    if slices is None:
+        return None, 0
+    s = np.ascontiguousarray(np.asarray(slices, np.int32).reshape(-1, 2))
+    return s, len(s)
+
+
+def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != torch.float64:
+        raise ValueError(f"{name} must be a float64 CUDA tensor (there is no CPU path)")
+    return t.contiguous()
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def batch_config_dist(q: torch.Tensor, pts: torch.Tensor, slices=None, metric: str = "max") -> torch.Tensor:
+    """One-to-many distance, [N] float64 (configuration.py:303-329)."""
+    lib = _lib.load()
+    q, pts = _f64(q.reshape(-1), "q"), _f64(pts, "pts")
+    N, D = pts.shape
+    if q.numel() != D:
+        raise ValueError("dimension mismatch")
+    s, R = _slices(slices)
+    out = torch.empty(N, dtype=torch.float64, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _lib.check(lib.mrb200_batch_dist(q.data_ptr(), pts.data_ptr(), N, D, s.ctypes.data_as(_lib.c_i32p) if s is not None else None,
+                                         R, METRICS[metric], out.data_ptr(), _stream(pts.device)), "batch_dist")
+    return out
+
+
+def prm_k_star(N: int, D: int) -> int:
+    """k* = int(e (1 + 1/D) ln N) + 1, clipped to N (prm_graph.py:440-445)."""
+    return min(int(math.e * (1 + 1 / D) * math.log(N)) + 1, N) if N > 0 else 0
+
+
+def prm_r_star(N: int, D: int, informed_measure: float = 1.0) -> float:
+    """PRM* connection radius (prm_graph.py:479-498)."""
+    if N <= 1:
+        return 1e6
+    unit_ball = (math.pi ** 0.5) ** D / math.gamma(D / 2 + 1)
+    return 1.001 * 2 * (informed_measure / unit_ball * (math.log(N) / N) * (1 + 1 / D)) ** (1 / D)
+
+
+def batch_knn(queries: torch.Tensor, corpus: torch.Tensor, slices=None, metric: str = "max_euclidean", k: int = 1,
+              mode: str = "auto", return_dist: bool = True):
+    """k nearest corpus rows of every query row, ascending (distance, index).
+    -> (idx [Q, k] int32, dist [Q, k] float64); missing neighbours are -1 / inf."""
+    lib = _lib.load()
+    queries, corpus = _f64(queries, "queries"), _f64(corpus, "corpus")
+    Q, D = queries.shape
+    N = corpus.shape[0]
+    if corpus.shape[1] != D:
+        raise ValueError("dimension mismatch")
+    s, R = _slices(slices)
+    dev = queries.device
+    idx = torch.empty(Q, k, dtype=torch.int32, device=dev)
+    dist = torch.empty(Q, k, dtype=torch.float64, device=dev) if return_dist else None
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.mrb200_knn_workspace_bytes(Q, N, D, k))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.mrb200_knn(queries.data_ptr(), corpus.data_ptr(), Q, N, D,
+                                  s.ctypes.data_as(_lib.c_i32p) if s is not None else None, R, METRICS[metric], int(k),
+                                  idx.data_ptr(), dist.data_ptr() if dist is not None else None, ws.data_ptr(), ws_bytes,
+                                  {"auto": 0, "exact": 1, "tensor": 2}[mode], _stream(dev)), "knn")
+    return (idx, dist) if return_dist else idx
+
+
+def batch_radius(queries: torch.Tensor, corpus: torch.Tensor, radius: Union[float, torch.Tensor], slices=None,
+                 metric: str = "max_euclidean", inclusive: bool = False, return_dist: bool = False):
+    """Radius neighbours in CSR form, indices ascending per row (the reference's np.where order).
+    inclusive=False: d < r (PRM, prm_graph.py:500); True: d <= r + 1e-10 (RRT*/IT*).
+    -> (offsets [Q+1] int64, indices int32 [, dists float64])"""
+    lib = _lib.load()
+    queries, corpus = _f64(queries, "queries"), _f64(corpus, "corpus")
+    Q, D = queries.shape
+    N = corpus.shape[0]
+    s, R = _slices(slices)
+    sp = s.ctypes.data_as(_lib.c_i32p) if s is not None else None
+    dev = queries.device
+    radii = None
+    r = 0.0
+    if isinstance(radius, torch.Tensor):
+        radii = _f64(radius.reshape(-1), "radius")
+        if radii.numel() != Q:
+            raise ValueError("one radius per query expected")
+    else:
+        r = float(radius)
+    with torch.cuda.device(dev):
+        splits = int(lib.mrb200_radius_splits(Q, N))
+        counts = torch.zeros(Q * splits, dtype=torch.int64, device=dev)
+        args = (queries.data_ptr(), corpus.data_ptr(), Q, N, D, sp, R, METRICS[metric],
+                radii.data_ptr() if radii is not None else None, r, int(inclusive), splits)
+        _lib.check(lib.mrb200_radius_count(*args, counts.data_ptr(), _stream(dev)), "radius_count")
+        ends = torch.cumsum(counts, 0)           # plumbing: the scan between the two launches
+        offs = ends - counts
+        total = int(ends[-1].item()) if Q else 0
+        idx = torch.empty(total, dtype=torch.int32, device=dev)
+        dist = torch.empty(total, dtype=torch.float64, device=dev) if return_dist else None
+        if total:
+            _lib.check(lib.mrb200_radius_fill(*args, offs.data_ptr(), idx.data_ptr(), dist.data_ptr() if dist is not None else None,
+                                              _stream(dev)), "radius_fill")
+        row_off = torch.cat([offs.view(Q, splits)[:, 0], ends[-1:]]) if Q else torch.zeros(1, dtype=torch.int64, device=dev)
+    return (row_off, idx, dist) if return_dist else (row_off, idx)

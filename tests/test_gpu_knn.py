@@ -1,0 +1,94 @@
+"""GPU parity of the distance / neighbour kernels against golden vectors produced by the unmodified
+reference (tests/golden/abstract_golden.npz) and against the numpy oracle.  Distances: the reference's
+numba kernels are fastmath, so fp64 values are compared to 2 ulp; indices are bit-exact (ties broken
+by index, which random data never exercises)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_abstract as OA
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def knn(cuda_lib):
+    from multirobot_pathplanning_benchmark_b200 import knn as K
+    return K
+
+
+@pytest.mark.parametrize("name", ["d22", "d77", "d333", "d25", "d14", "d6666"])
+def test_batch_dist_matches_reference_golden(knn, golden, name):
+    q, pts, sl = golden[f"met_{name}_q"], golden[f"met_{name}_pts"], golden[f"met_{name}_slices"]
+    for metric in ("euclidean", "sum_euclidean", "max_euclidean", "max"):
+        got = knn.batch_config_dist(torch.from_numpy(q).cuda(), torch.from_numpy(pts).cuda(), sl, metric).cpu().numpy()
+        assert np.allclose(got, golden[f"met_{name}_dist_{metric}"], rtol=4e-16, atol=0)
+        assert np.array_equal(got, OA.batch_config_dist(q, pts, sl, metric))  # same operand order as the oracle: bit-exact
+
+
+@pytest.mark.parametrize("metric", ["max_euclidean", "euclidean", "sum_euclidean", "max"])
+@pytest.mark.parametrize("mode", ["exact", "auto"])
+def test_knn_matches_reference_golden(knn, golden, metric, mode):
+    corpus, qidx, sl, k = golden["knn_corpus"], golden["knn_qidx"], golden["knn_slices"], int(golden["knn_k"])
+    c = torch.from_numpy(corpus).cuda()
+    idx, dist = knn.batch_knn(c[torch.from_numpy(qidx).cuda()], c, sl, metric, k, mode=mode)
+    assert np.array_equal(idx.cpu().numpy(), golden[f"knn_idx_{metric}"])
+    assert (np.diff(dist.cpu().numpy(), axis=1) >= 0).all()
+
+
+@pytest.mark.parametrize("metric", ["max_euclidean", "euclidean"])
+def test_radius_matches_reference_golden(knn, golden, metric):
+    corpus, qidx, sl = golden["knn_corpus"], golden["knn_qidx"], golden["knn_slices"]
+    rr, rcnt, ridx = golden[f"knn_rad_r_{metric}"], golden[f"knn_rad_cnt_{metric}"], golden[f"knn_rad_idx_{metric}"]
+    c = torch.from_numpy(corpus).cuda()
+    off, idx, dist = knn.batch_radius(c[torch.from_numpy(qidx).cuda()], c, torch.from_numpy(rr).cuda(), sl, metric, return_dist=True)
+    off, idx, dist = off.cpu().numpy(), idx.cpu().numpy(), dist.cpu().numpy()
+    o = 0
+    for j in range(len(qidx)):
+        got, d = idx[off[j]:off[j + 1]], dist[off[j]:off[j + 1]]
+        assert (np.diff(got) > 0).all()  # ascending index order, like np.where
+        tie = set(got[np.abs(d - rr[j]) <= 4 * np.finfo(np.float64).eps * rr[j]])
+        ref = set(ridx[o:o + rcnt[j]])
+        # the golden radius is itself one of the reference's (fastmath, 1-ulp) distances
+        assert (set(got) ^ ref) <= tie | {i for i in ref if abs(OA.batch_config_dist(corpus[qidx[j]], corpus[i:i + 1], sl, metric)[0] - rr[j]) <= 4e-16 * rr[j]}
+        o += rcnt[j]
+
+
+@pytest.mark.parametrize("Q,N,D,k", [(1, 5000, 6, 7), (300, 257, 12, 33), (129, 20000, 24, 33), (1000, 3, 4, 5), (64, 1, 6, 1)])
+def test_knn_shapes_against_oracle(knn, Q, N, D, k):
+    rng = np.random.default_rng(Q + N)
+    sl = np.array([[s, s + D // 2] for s in (0, D // 2)])
+    corpus, queries = rng.uniform(-3, 3, (N, D)), rng.uniform(-3, 3, (Q, D))
+    for metric in ("max_euclidean", "euclidean", "max"):
+        idx, dist = knn.batch_knn(torch.from_numpy(queries).cuda(), torch.from_numpy(corpus).cuda(), sl, metric, k)
+        idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+        for j in range(0, Q, max(1, Q // 25)):
+            d = OA.batch_config_dist(queries[j], corpus, sl, metric)
+            want = OA.knn_indices(d, k)
+            assert np.array_equal(idx[j, :len(want)], want)
+            assert (idx[j, len(want):] == -1).all() and np.isinf(dist[j, len(want):]).all()
+            assert np.array_equal(dist[j, :len(want)], d[want])
+
+
+def test_knn_ties_break_by_index(knn):
+    corpus = np.zeros((100, 4))
+    corpus[50:] = 1.0
+    q = np.zeros((3, 4))
+    idx, _ = knn.batch_knn(torch.from_numpy(q).cuda(), torch.from_numpy(corpus).cuda(), [[0, 2], [2, 4]], "max_euclidean", 10)
+    assert np.array_equal(idx.cpu().numpy(), np.tile(np.arange(10), (3, 1)))
+
+
+def test_radius_inclusive_and_scalar(knn):
+    rng = np.random.default_rng(3)
+    corpus, queries = rng.uniform(-1, 1, (5000, 6)), rng.uniform(-1, 1, (70, 6))
+    sl = [[0, 3], [3, 6]]
+    for inclusive in (False, True):
+        off, idx = knn.batch_radius(torch.from_numpy(queries).cuda(), torch.from_numpy(corpus).cuda(), 0.5, sl, "max_euclidean",
+                                    inclusive=inclusive)
+        off, idx = off.cpu().numpy(), idx.cpu().numpy()
+        for j in range(len(queries)):
+            d = OA.batch_config_dist(queries[j], corpus, np.array(sl), "max_euclidean")
+            want = OA.radius_indices(d, 0.5, 1e-10 if inclusive else None)
+            assert np.array_equal(idx[off[j]:off[j + 1]], want)
+    off, idx = knn.batch_radius(torch.from_numpy(queries).cuda(), torch.from_numpy(corpus).cuda(), 1e-9, sl, "euclidean")
+    assert off[-1].item() == 0
