@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmrb200.so")
-SOURCES = ["capi.cu", "scene_kernels.cu", "abstract_kernels.cu", "knn_kernels.cu"]
+SOURCES = ["capi.cu", "scene_kernels.cu", "abstract_kernels.cu", "knn_kernels.cu", "knn_tc_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # --use_fast_math would also turn sincosf/sqrtf/division into approximations; the kernels ask

@@ -312,10 +312,38 @@ int mrb200_batch_dist(const double* q, const double* pts, int64_t N, int D, cons
     return MRB200_OK;
 }
 
+// candidates kept per row by the tensor-core path
+static int tc_candidates(int k) { return k + 16; }
+
+static bool tc_usable(int64_t Q, int64_t N, int D, const mrb::Slices& sl, int metric, int k, mrb::TcPlan* plan) {
+    if (k > 48 || N < 1024 || Q < 1) return false;
+    if (!mrb::knn_tc_make_plan(D, sl, metric, plan)) return false;
+    // narrower corpus tiles until query tile + 3 corpus stages + candidate heaps fit in shared memory
+    while (plan->tn > 32 && mrb::knn_tc_smem_bytes(*plan, tc_candidates(k)) > 200 * 1024) plan->tn >>= 1;
+    return mrb::knn_tc_smem_bytes(*plan, tc_candidates(k)) <= 200 * 1024;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
 size_t mrb200_knn_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
-    if (Q <= 0 || k <= 0) return 16;
+    if (Q <= 0 || k <= 0) return 256;
     const int splits = mrb::knn_pick_splits(Q, N);
-    return (size_t)splits * (size_t)Q * (size_t)k * 12 + 256;
+    size_t exact = align256((size_t)splits * (size_t)Q * (size_t)k * 12 + 256);
+    // the tensor-core path needs its operands, candidate lists and certification flags as well; size for
+    // the worst plan (one accumulator per dimension pair is never worse than 8 accumulators of 32 columns)
+    mrb::Slices sl{};
+    mrb::TcPlan plan;
+    size_t tc = 0;
+    if (mrb::knn_tc_make_plan(D, sl, MRB200_METRIC_EUCLIDEAN, &plan)) {
+        // euclidean has the largest K padding; max_euclidean plans use at most the same K steps + 1 per robot
+        mrb::TcPlan worst = plan;
+        worst.KS = plan.KS + mrb::KNN_MAX_R;
+        worst.tn = 256;
+        const int64_t ct = (N + 31) / 32;  // smallest tile width -> most tiles
+        tc = align256((size_t)((Q + 127) / 128) * worst.KS * 128 * 32) + align256((size_t)ct * worst.KS * 32 * 32) +
+             align256((size_t)32 * Q * tc_candidates(k) * 8) + align256((size_t)Q) + 4096;
+    }
+    return exact + tc;
 }
 
 int mrb200_knn(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const int32_t* slices_host, int R, int metric,
@@ -326,12 +354,29 @@ int mrb200_knn(const double* queries, const double* corpus, int64_t Q, int64_t N
         return fail(MRB200_ERR_ARG, "knn: bad argument (k must be in [1, 128])");
     if (Q == 0) return MRB200_OK;
     if (workspace_bytes < mrb200_knn_workspace_bytes(Q, N, D, k) || !workspace) return fail(MRB200_ERR_ARG, "knn: workspace too small");
-    if (mode == 2) return fail(MRB200_ERR_ARG, "knn: tensor-core path not available for this metric / build");
+    cudaStream_t st = (cudaStream_t)stream;
     const int splits = mrb::knn_pick_splits(Q, N);
     double* part_d = (double*)workspace;
     int* part_i = (int*)(part_d + (size_t)splits * Q * k);
-    cudaError_t e = mrb::launch_knn_exact(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, out_idx, out_dist,
-                                          (cudaStream_t)stream);
+    unsigned char* tc_ws = (unsigned char*)workspace + align256((size_t)splits * (size_t)Q * (size_t)k * 12 + 256);
+    mrb::TcPlan plan;
+    const bool tc_ok = tc_usable(Q, N, D, sl, metric, k, &plan);
+    if (mode == 2 && !tc_ok) return fail(MRB200_ERR_ARG, "knn: the tensor-core path needs metric euclidean / max_euclidean, k <= 48, N >= 1024");
+    const bool use_tc = mode == 2 || (mode == 0 && tc_ok && Q >= 256 && N >= 4096);
+    const uint8_t* skip = nullptr;
+    if (use_tc) {
+        const int kc = tc_candidates(k);
+        const int64_t ct = (N + plan.tn - 1) / plan.tn;
+        const int tsplits = mrb::knn_tc_splits(Q, ct);
+        uint8_t* certified = tc_ws;
+        cudaError_t e = mrb::launch_knn_tc(queries, corpus, Q, N, D, sl, metric, k, kc, plan, tsplits, tc_ws + align256((size_t)Q), out_idx,
+                                           out_dist, certified, st);
+        if (e != cudaSuccess) return cuda_fail(e, "knn (tensor-core path)");
+        g_launches += 4;
+        skip = certified;  // rows the re-rank could not certify are recomputed exactly below
+    }
+    cudaError_t e = mrb::launch_knn_exact(queries, corpus, Q, N, D, sl, metric, k, use_tc ? 1 : splits, part_d, part_i, out_idx, out_dist,
+                                          skip, st);
     if (e != cudaSuccess) return cuda_fail(e, "knn");
     g_launches += 2;
     return MRB200_OK;

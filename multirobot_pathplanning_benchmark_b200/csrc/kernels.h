@@ -69,7 +69,17 @@ int knn_pick_splits(int64_t Q, int64_t N);
 cudaError_t launch_batch_dist(const double* q, const double* pts, int64_t N, int D, const Slices& sl, int metric, double* out,
                               cudaStream_t st);
 cudaError_t launch_knn_exact(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
-                             int k, int splits, double* part_d, int* part_i, int32_t* out_idx, double* out_dist, cudaStream_t st);
+                             int k, int splits, double* part_d, int* part_i, int32_t* out_idx, double* out_dist, const uint8_t* skip,
+                             cudaStream_t st);
+// tensor-core candidate generator + exact re-rank (knn_tc_kernels.cu)
+struct TcPlan;
+bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan);
+size_t knn_tc_smem_bytes(const TcPlan& plan, int kc);
+int knn_tc_splits(int64_t Q, int64_t n_ctiles);
+size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, int splits);
+cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
+                          int k, int kc, const TcPlan& plan, int splits, void* workspace, int32_t* out_idx, double* out_dist,
+                          uint8_t* certified, cudaStream_t st);
 cudaError_t launch_radius(bool fill, const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl,
                           int metric, const double* radii, double radius, int inclusive, int splits, int64_t* counts,
                           const int64_t* offsets, int32_t* out_idx, double* out_dist, cudaStream_t st);

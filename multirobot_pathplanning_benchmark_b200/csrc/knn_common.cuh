@@ -22,6 +22,17 @@ struct Slices {
     int end[KNN_MAX_R];
 };
 
+// operand plan of the tensor-core candidate generator (knn_tc_kernels.cu)
+struct TcPlan {
+    int n_acc;               // accumulators = robot slices (1 for euclidean)
+    int start[KNN_MAX_R];    // slice of each accumulator
+    int dim[KNN_MAX_R];
+    int kstep0[KNN_MAX_R];   // first K step (of 8) of each accumulator
+    int ksteps[KNN_MAX_R];
+    int KS;                  // total K steps
+    int tn;                  // corpus columns per accumulator tile (UMMA N)
+};
+
 // distance between q (registers / local) and p (any memory), fp64, reference operand order:
 // diff = q - p; per-slice sum of squares left to right; sqrt; reduce over slices
 template <int DMAX>

@@ -89,7 +89,7 @@ template <int DMAX>
 __global__ void __launch_bounds__(KT) knn_exact_kernel(const double* __restrict__ queries, const double* __restrict__ corpus, int64_t Q,
                                                        int64_t N, int D, const __grid_constant__ Slices sl, int metric, int k,
                                                        int64_t split_len, double* __restrict__ part_d, int* __restrict__ part_i,
-                                                       int bulk_ok) {
+                                                       int bulk_ok, const uint8_t* __restrict__ skip) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);                  // [2][TN][D]
     double* hk = tiles + (size_t)2 * TN * D;                                // [k][KT]
@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(KT) knn_exact_kernel(const double* __restrict_
     }
     __syncthreads();
     const int64_t row = blockIdx.x * (int64_t)KT + threadIdx.x;
-    const bool valid = row < Q;
+    // rows flagged in `skip` (already answered and certified by the tensor-core path) are left alone
+    const bool valid = row < Q && !(skip && skip[row]);
+    if (!__syncthreads_or(valid)) return;
     double q[DMAX];
 #pragma unroll
     for (int d = 0; d < DMAX; d++) q[d] = (valid && d < D) ? queries[row * D + d] : 0.0;
@@ -123,12 +125,13 @@ __global__ void __launch_bounds__(KT) knn_exact_kernel(const double* __restrict_
 
 // merge the partial lists of one row and emit the k nearest in ascending (distance, index) order
 __global__ void __launch_bounds__(KT) knn_merge_kernel(const double* __restrict__ part_d, const int* __restrict__ part_i, int64_t Q, int k,
-                                                       int splits, int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+                                                       int splits, int32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                                       const uint8_t* __restrict__ skip) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* hk = reinterpret_cast<double*>(smem_raw);
     int* hi = reinterpret_cast<int*>(hk + (size_t)k * KT);
     const int64_t row = blockIdx.x * (int64_t)KT + threadIdx.x;
-    if (row >= Q) return;
+    if (row >= Q || (skip && skip[row])) return;
     ThreadHeap<double> heap{hk + threadIdx.x, hi + threadIdx.x, KT, k, 0};
     for (int s = 0; s < splits; s++) {
         const double* pd = part_d + ((size_t)s * Q + row) * k;
@@ -228,31 +231,32 @@ cudaError_t launch_batch_dist(const double* q, const double* pts, int64_t N, int
 
 template <int DMAX>
 static cudaError_t knn_exact_t(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
-                               int k, int splits, double* part_d, int* part_i, int bulk_ok, cudaStream_t st) {
+                               int k, int splits, double* part_d, int* part_i, int bulk_ok, const uint8_t* skip, cudaStream_t st) {
     const size_t smem = (size_t)2 * TN * D * 8 + (size_t)k * KT * 12 + 16;
     cudaError_t e = cudaFuncSetAttribute(knn_exact_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t split_len = ((N + splits - 1) / splits + TN - 1) / TN * TN;
     dim3 grid((unsigned)((Q + KT - 1) / KT), (unsigned)splits);
-    knn_exact_kernel<DMAX><<<grid, KT, smem, st>>>(queries, corpus, Q, N, D, sl, metric, k, split_len, part_d, part_i, bulk_ok);
+    knn_exact_kernel<DMAX><<<grid, KT, smem, st>>>(queries, corpus, Q, N, D, sl, metric, k, split_len, part_d, part_i, bulk_ok, skip);
     return cudaGetLastError();
 }
 
 cudaError_t launch_knn_exact(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
-                             int k, int splits, double* part_d, int* part_i, int32_t* out_idx, double* out_dist, cudaStream_t st) {
+                             int k, int splits, double* part_d, int* part_i, int32_t* out_idx, double* out_dist, const uint8_t* skip,
+                             cudaStream_t st) {
     if (Q <= 0) return cudaSuccess;
     const int bulk_ok = (((uintptr_t)corpus) & 15) == 0;
     cudaError_t e;
-    if (D <= 8) e = knn_exact_t<8>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, st);
-    else if (D <= 16) e = knn_exact_t<16>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, st);
-    else if (D <= 24) e = knn_exact_t<24>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, st);
-    else if (D <= 32) e = knn_exact_t<32>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, st);
-    else e = knn_exact_t<64>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, st);
+    if (D <= 8) e = knn_exact_t<8>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, skip, st);
+    else if (D <= 16) e = knn_exact_t<16>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, skip, st);
+    else if (D <= 24) e = knn_exact_t<24>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, skip, st);
+    else if (D <= 32) e = knn_exact_t<32>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, skip, st);
+    else e = knn_exact_t<64>(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, bulk_ok, skip, st);
     if (e != cudaSuccess) return e;
     const size_t smem = (size_t)k * KT * 12;
     e = cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    knn_merge_kernel<<<(unsigned)((Q + KT - 1) / KT), KT, smem, st>>>(part_d, part_i, Q, k, splits, out_idx, out_dist);
+    knn_merge_kernel<<<(unsigned)((Q + KT - 1) / KT), KT, smem, st>>>(part_d, part_i, Q, k, splits, out_idx, out_dist, skip);
     return cudaGetLastError();
 }
 

@@ -27,8 +27,10 @@ def test_batch_dist_matches_reference_golden(knn, golden, name):
 
 
 @pytest.mark.parametrize("metric", ["max_euclidean", "euclidean", "sum_euclidean", "max"])
-@pytest.mark.parametrize("mode", ["exact", "auto"])
+@pytest.mark.parametrize("mode", ["exact", "auto", "tensor"])
 def test_knn_matches_reference_golden(knn, golden, metric, mode):
+    if mode == "tensor" and metric not in ("euclidean", "max_euclidean"):
+        pytest.skip("the tcgen05 candidate generator covers the contraction-shaped metrics only")
     corpus, qidx, sl, k = golden["knn_corpus"], golden["knn_qidx"], golden["knn_slices"], int(golden["knn_k"])
     c = torch.from_numpy(corpus).cuda()
     idx, dist = knn.batch_knn(c[torch.from_numpy(qidx).cuda()], c, sl, metric, k, mode=mode)
@@ -92,3 +94,33 @@ def test_radius_inclusive_and_scalar(knn):
             assert np.array_equal(idx[off[j]:off[j + 1]], want)
     off, idx = knn.batch_radius(torch.from_numpy(queries).cuda(), torch.from_numpy(corpus).cuda(), 1e-9, sl, "euclidean")
     assert off[-1].item() == 0
+
+
+@pytest.mark.parametrize("metric,R", [("max_euclidean", 4), ("max_euclidean", 2), ("euclidean", 1), ("max_euclidean", 3)])
+def test_tensor_core_path_equals_exact_path(knn, metric, R):
+    """tcgen05 candidates + fp64 re-rank must return exactly what the fp64 CUDA-core path returns."""
+    rng = np.random.default_rng(11 + R)
+    D = 6 * R if R > 1 else 24
+    sl = [[6 * r, 6 * r + 6] for r in range(R)] if R > 1 else None
+    N, Q, k = 30011, 1531, 33
+    corpus = rng.uniform(-3.2, 3.2, (N, D))
+    queries = np.vstack([corpus[rng.choice(N, Q // 2, replace=False)], rng.uniform(-3.2, 3.2, (Q - Q // 2, D))])
+    c, q = torch.from_numpy(corpus).cuda(), torch.from_numpy(queries).cuda()
+    i_t, d_t = knn.batch_knn(q, c, sl, metric, k, mode="tensor")
+    i_e, d_e = knn.batch_knn(q, c, sl, metric, k, mode="exact")
+    assert torch.equal(i_t, i_e)
+    assert torch.equal(d_t, d_e)
+
+
+def test_tensor_core_path_with_duplicates_falls_back_exactly(knn):
+    """Rows the re-rank cannot certify (more ties than slack candidates) are recomputed by the exact kernel."""
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-2, 2, (40, 12))
+    corpus = np.repeat(base, 100, axis=0)  # every point 100 times
+    q = torch.from_numpy(base).cuda()
+    c = torch.from_numpy(corpus).cuda()
+    sl = [[0, 6], [6, 12]]
+    i_t, d_t = knn.batch_knn(q, c, sl, "max_euclidean", 30, mode="tensor")
+    i_e, d_e = knn.batch_knn(q, c, sl, "max_euclidean", 30, mode="exact")
+    assert torch.equal(i_t, i_e) and torch.equal(d_t, d_e)
+    assert (d_t == 0).all()
