@@ -335,6 +335,29 @@ def main():
             if wname == args.workload:
                 edge_inputs = (q1.cpu().numpy(), q2.cpu().numpy())
             del qd, q1, q2
+        # BASELINE config 4: batched k-NN for PRM/EIT graph building, 100k samples of one mode, D = 24
+        from multirobot_pathplanning_benchmark_b200 import knn as K
+        Nk, Dk, kk = 100_000, 24, K.prm_k_star(100_000, 24)
+        slk = [[6 * r, 6 * r + 6] for r in range(4)]
+        limk = SCENES["box_stacking"][0]().limits()
+        corpus = torch.from_numpy(np.random.RandomState(5).uniform(limk[0], limk[1], (Nk, Dk))).to(dev)
+        knn_res = {"N": Nk, "Q": Nk, "D": Dk, "k": kk, "metric": "max_euclidean"}
+        for mode in ("tensor", "exact"):
+            K.batch_knn(corpus[:4096], corpus, slk, "max_euclidean", kk, mode=mode)
+            tk = timed(lambda: K.batch_knn(corpus, corpus, slk, "max_euclidean", kk, mode=mode), 2)
+            knn_res[f"{mode}_queries_per_s"] = Nk / tk
+            knn_res[f"{mode}_ms"] = tk * 1e3
+        knn_res["tensor_algorithmic_tflops"] = 2.0 * Nk * Nk * Dk / (knn_res["tensor_ms"] * 1e-3) / 1e12
+        if not args.no_cpu:
+            from oracle import oracle_abstract as OA
+            cn = corpus.cpu().numpy()
+            t = time.perf_counter()
+            nq = 40
+            for j in range(nq):
+                OA.knn_indices(OA.batch_config_dist(cn[j], cn, np.array(slk), "max_euclidean"), kk)
+            knn_res["cpu_port_queries_per_s_1core"] = nq / (time.perf_counter() - t)
+        extra["knn_box_stacking_100k"] = knn_res
+        del corpus
     else:
         edge_inputs = None
 

@@ -1,0 +1,436 @@
+"""`B200Env`: the reference's environment interface on top of the CUDA backend.
+
+The reference's planners talk to an environment only through `BaseProblem`
+(P/problems/planning_env.py:1531-1994, P/ = src/multi_robot_multi_goal_planning/); backends are
+classes registered with `@register("name")` (P/problems/core/registry.py:8-25).  This module
+defines such classes for the B200 backend.  When the reference package is importable they derive
+from its `BaseProblem` and mode-logic mixins (exactly like `rai_envs.py:573` composes
+`SequenceMixin` with `rai_env`) and are registered as `b200.*`; without it the geometry / batch
+API of `SceneModel` is still usable on its own (that is what the GPU tests and bench.py use).
+
+Collision queries never run on the host: `SceneModel` owns a device (by default the CUDA
+`SceneBackend`; it raises if libmrb200.so or a GPU is missing).  Tests may inject another device
+object with the same four methods to exercise the host logic on a CPU-only machine.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .scene import CompiledScene, Scene, compile_blob
+from .scenes import SCENES
+
+try:  # the reference package (optional at import time)
+    from multi_robot_multi_goal_planning.problems.planning_env import (  # type: ignore
+        BaseModeLogic, BaseProblem, Mode, SequenceMixin, State, Task, ProblemSpec, AgentType, ConstraintType,
+        ManipulationType, DependencyType, DynamicsType, GoalType, SafePoseType, generate_binary_search_indices)
+    from multi_robot_multi_goal_planning.problems.core.configuration import (  # type: ignore
+        NpConfiguration, batch_config_cost, config_cost, config_dist)
+    from multi_robot_multi_goal_planning.problems.core.goals import GoalSet, SingleGoal  # type: ignore
+    from multi_robot_multi_goal_planning.problems.core.registry import register  # type: ignore
+    HAVE_REFERENCE = True
+except Exception:  # pragma: no cover - exercised on machines without the reference
+    HAVE_REFERENCE = False
+    BaseProblem = object  # type: ignore
+
+    def register(_names):  # type: ignore
+        return lambda cls: cls
+
+
+# ----------------------------------------------------------------------------------------------
+# devices
+# ----------------------------------------------------------------------------------------------
+class CudaDevice:
+    """numpy-in / numpy-out adapter over backend.SceneBackend for the single-query API; the batch
+    API hands CUDA tensors straight through."""
+
+    def __init__(self, max_modes: int = 256, device=None):
+        import torch
+        from .backend import SceneBackend
+        self.torch = torch
+        self.be = SceneBackend(max_modes=max_modes, device=device)
+        self.dev = self.be.device
+
+    def set_mode(self, slot: int, cs: CompiledScene) -> None:
+        self.be.set_mode(slot, cs)
+
+    def _t(self, a, dtype=None):
+        t = self.torch
+        if isinstance(a, t.Tensor):
+            return a
+        return t.from_numpy(np.ascontiguousarray(a, np.float32)).to(self.dev)
+
+    def check_configs(self, slot, q, tol=None):
+        return self.be.check_configs(slot, self._t(q), tol=tol)
+
+    def check_configs_for_robot(self, slot, q, rel, oth, tol=None):
+        return self.be.check_configs_for_robot(slot, self._t(q), rel, oth, tol=tol)
+
+    def check_edges(self, slot, q1, q2, resolution, N=None, n_start=0, n_max=None, include_endpoints=False, tol=None):
+        t = self.torch
+        if N is not None and not isinstance(N, t.Tensor):
+            N = t.from_numpy(np.ascontiguousarray(N, np.int32)).to(self.dev)
+        return self.be.check_edges(slot, self._t(q1), self._t(q2), resolution, N=N, n_start=n_start, n_max=n_max,
+                                   include_endpoints=include_endpoints, tol=tol)
+
+    @staticmethod
+    def to_numpy(x):
+        return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+
+
+# ----------------------------------------------------------------------------------------------
+# geometry + modes, independent of the reference package
+# ----------------------------------------------------------------------------------------------
+class SceneModel:
+    """A primitive scene, its per-mode kinematic trees and the device that checks them.
+
+    A mode's tree is the base scene plus a chain of relinks (parent, child, configuration at
+    which the child was attached) -- what rai_env.set_to_mode replays
+    (P/problems/rai_base_env.py:704-836).  Each distinct tree is compiled once into a blob and
+    uploaded into a device slot."""
+
+    def __init__(self, scene: Scene, tol: float, resolution: float, device=None, max_modes: int = 256):
+        self.base = scene
+        self.tol = float(tol)
+        self.resolution = float(resolution)
+        self.max_modes = max_modes
+        self._device = device
+        self._slots: Dict[tuple, int] = {}
+        self._compiled: Dict[int, CompiledScene] = {}
+        self._scenes: Dict[int, Scene] = {}
+
+    @property
+    def device(self):
+        if self._device is None:
+            self._device = CudaDevice(self.max_modes)  # raises without libmrb200.so / a GPU: no CPU fallback
+        return self._device
+
+    def relinked(self, relinks: Sequence[Tuple[str, str, np.ndarray]]) -> Scene:
+        sc = self.base.copy()
+        for parent, child, q in relinks:
+            sc.attach(parent, child, np.asarray(q, np.float64))
+        return sc
+
+    def slot_for(self, key: tuple, relinks: Sequence[Tuple[str, str, np.ndarray]] = ()) -> int:
+        if key not in self._slots:
+            if len(self._slots) >= self.max_modes:
+                raise RuntimeError(f"more than {self.max_modes} distinct kinematic trees; raise max_modes")
+            slot = len(self._slots)
+            sc = self.relinked(relinks)
+            cs = compile_blob(sc, self.tol)
+            self.device.set_mode(slot, cs)
+            self._slots[key] = slot
+            self._compiled[slot] = cs
+            self._scenes[slot] = sc
+        return self._slots[key]
+
+    def compiled(self, slot: int) -> CompiledScene:
+        return self._compiled[slot]
+
+    def scene(self, slot: int) -> Scene:
+        return self._scenes[slot]
+
+    # batch API (arrays or CUDA tensors in, device results out)
+    def check_configs(self, slot, qs, tol=None):
+        return self.device.check_configs(slot, qs, tol)
+
+    def check_edges(self, slot, q1s, q2s, resolution=None, **kw):
+        return self.device.check_edges(slot, q1s, q2s, self.resolution if resolution is None else resolution, **kw)
+
+
+if HAVE_REFERENCE:
+
+    class B200Env(BaseProblem):
+        """Primitive-scene environment answering the reference's collision API from the GPU.
+
+        Same contract as rai_env (P/problems/rai_base_env.py:258-836): `is_collision_free`
+        raises ValueError on q=None like abstract_env.py:256-257; a failing device call raises
+        (never reports "free")."""
+
+        def __init__(self, scene: Scene, tol: float, resolution: float, device=None):
+            self.model = SceneModel(scene, tol, resolution, device=device)
+            self.scene = scene
+            self.robots = list(scene.robots)
+            sl = scene.robot_slices()
+            self.robot_idx = {r: list(range(sl[r][0], sl[r][1])) for r in self.robots}
+            self.robot_dims = {r: sl[r][1] - sl[r][0] for r in self.robots}
+            home = scene.home()
+            self.start_pos = NpConfiguration.from_list([home[sl[r][0]:sl[r][1]] for r in self.robots])
+            self.limits = scene.limits()
+            self.collision_tolerance = tol
+            self.collision_resolution = resolution
+            self.cost_metric = "euclidean"
+            self.cost_reduction = "max"
+            self.manipulating_env = False
+            self.prev_mode = None
+            self._slot = None
+            super().__init__()
+            self.spec = ProblemSpec(agent_type=AgentType.MULTI_AGENT, constraints=ConstraintType.UNCONSTRAINED,
+                                    manipulation=ManipulationType.MANIPULATION, dependency=DependencyType.FULLY_ORDERED,
+                                    dynamics=DynamicsType.GEOMETRIC, goals=GoalType.MULTI_GOAL,
+                                    home_pose=SafePoseType.HAS_NO_SAFE_HOME_POSE)
+
+        # ---- visualisation: no-ops -------------------------------------------------------
+        def show(self, blocking: bool = False) -> None:
+            pass
+
+        def show_config(self, q, blocking: bool = True) -> None:
+            pass
+
+        def display_path(self, *a, **k) -> None:
+            pass
+
+        # ---- costs: the reference's own kernels (small batches, host) ----------------------
+        def config_cost(self, start, end) -> float:
+            return config_cost(start, end, self.cost_metric, self.cost_reduction)
+
+        def batch_config_cost(self, starts, ends, tmp_agent_slice=None):
+            return batch_config_cost(starts, ends, self.cost_metric, self.cost_reduction, tmp_agent_slice=tmp_agent_slice)
+
+        # ---- modes -------------------------------------------------------------------------
+        def _relinks_for_mode(self, m: "Mode") -> List[Tuple[str, str, np.ndarray]]:
+            """Replay of the mode chain, like rai_env.set_to_mode (rai_base_env.py:742-810): at every
+            past transition the switching robots sit at the next mode's entry configuration and the
+            finished task's frames[1] is attached to frames[0] (unless the task is a plain goto)."""
+            chain = []
+            cur = m
+            while cur is not None:
+                chain.append(cur)
+                cur = cur.prev_mode
+            chain = chain[::-1]
+            q = self.scene.home().copy()
+            relinks = []
+            for mode, nxt in zip(chain[:-1], chain[1:]):
+                task = self.get_active_task(mode, nxt.task_ids)
+                for r in task.robots:
+                    i = self.robots.index(r)
+                    q[self.robot_idx[r]] = nxt.entry_configuration[i]
+                done_task = self.tasks[mode.task_ids[self.robots.index(task.robots[0])]]
+                if done_task.type is not None and done_task.type != "goto":
+                    relinks.append((done_task.frames[0], done_task.frames[1], q.copy()))
+            return relinks
+
+        def _slot_for_mode(self, m: Optional["Mode"]) -> int:
+            if not self.manipulating_env or m is None:
+                return self.model.slot_for(())
+            relinks = self._relinks_for_mode(m)
+            key = tuple((p, c, np.round(q, 9).tobytes()) for p, c, q in relinks)
+            return self.model.slot_for(key, relinks)
+
+        def set_to_mode(self, m: "Mode", config=None, use_cached: bool = True, place_in_cache: bool = True):
+            if m is self.prev_mode and self._slot is not None:
+                return
+            self._slot = self._slot_for_mode(m)
+            self.prev_mode = m
+
+        def get_scenegraph_info_for_mode(self, mode: "Mode", is_start_mode: bool = False):
+            """{object: (parent name, rounded relative pose bytes)} (rai_base_env.py:678-702)."""
+            if not self.manipulating_env:
+                return {}
+            sc = self.model.relinked(self._relinks_for_mode(mode))
+            from .scene import mat_to_quat
+            sg = {}
+            for f in sc.frames.values():
+                if "obj" in f.name:
+                    pose = np.round(np.concatenate([f.rel.t, mat_to_quat(f.rel.R)]), 3)
+                    pose = np.where(np.abs(pose) < 1e-6, 0.0, pose)
+                    sg[f.name] = (f.parent, pose.tobytes())
+            mode._cached_hash = None
+            return sg
+
+        # ---- collision queries -------------------------------------------------------------
+        def is_collision_free(self, q, m, collision_tolerance: Optional[float] = None) -> bool:
+            if q is None:
+                raise ValueError
+            self.set_to_mode(m)
+            out = self.model.device.check_configs(self._slot, np.asarray(q.state(), np.float32)[None], collision_tolerance)
+            return bool(CudaDevice.to_numpy(out)[0])
+
+        def is_collision_free_np(self, q, m, collision_tolerance=None, set_mode: bool = True) -> bool:
+            if set_mode:
+                self.set_to_mode(m)
+            out = self.model.device.check_configs(self._slot, np.asarray(q, np.float32)[None], collision_tolerance)
+            return bool(CudaDevice.to_numpy(out)[0])
+
+        def _robot_masks(self, robots: List[str], m: "Mode"):
+            cs = self.model.compiled(self._slot)
+            frames = set()
+            for r in robots:
+                t = self.tasks[m.task_ids[self.robots.index(r)]]
+                if t.frames is not None:
+                    frames.update(t.frames)
+            others = [r for r in self.robots if r not in robots]
+            rel = np.array([any(r in n for r in robots) or n in frames for n in cs.shape_names], np.uint8)
+            oth = np.array([any(o in n for o in others) for n in cs.shape_names], np.uint8)
+            return rel, oth
+
+        def is_collision_free_for_robot(self, r, q, m=None, collision_tolerance=None, set_mode: bool = True) -> bool:
+            """rai_base_env.py:515-615: free unless the total penetration exceeds the tolerance AND some
+            penetrating pair involves robot r (or a frame of its task) and no other robot."""
+            if isinstance(r, str):
+                r = [r]
+            if set_mode:
+                self.set_to_mode(m)
+            rel, oth = self._robot_masks(list(r), m)
+            out = self.model.device.check_configs_for_robot(self._slot, np.asarray(q, np.float32)[None], rel, oth, collision_tolerance)
+            return bool(CudaDevice.to_numpy(out)[0])
+
+        def is_edge_collision_free(self, q1, q2, m, resolution=None, tolerance=None, include_endpoints: bool = False,
+                                   N_start: int = 0, N_max: Optional[int] = None, N: Optional[int] = None) -> bool:
+            """rai_base_env.py:618-676.  N is computed here in fp64 from the fp64 endpoints exactly like the
+            reference, then handed to the kernel."""
+            if resolution is None:
+                resolution = self.collision_resolution
+            if N is None:
+                N = max(2, int(config_dist(q1, q2, "max") / resolution) + 1)
+            if N_start > N:
+                assert False
+            self.set_to_mode(m)
+            free, _ = self.model.device.check_edges(
+                self._slot, np.asarray(q1.state(), np.float32)[None], np.asarray(q2.state(), np.float32)[None], resolution,
+                N=np.array([N], np.int32), n_start=N_start, n_max=N_max, include_endpoints=include_endpoints, tol=tolerance)
+            return bool(CudaDevice.to_numpy(free)[0])
+
+        # ---- additive batch variants (arrays or CUDA tensors in, device tensors out) -----------
+        def batch_is_collision_free(self, qs, mode):
+            self.set_to_mode(mode)
+            return self.model.check_configs(self._slot, qs)
+
+        def batch_is_edge_collision_free(self, q1s, q2s, mode, resolution=None, N_start: int = 0, N_max=None,
+                                         include_endpoints: bool = False):
+            self.set_to_mode(mode)
+            return self.model.check_edges(self._slot, q1s, q2s, resolution, n_start=N_start, n_max=N_max,
+                                          include_endpoints=include_endpoints)
+
+    def _two_dim_handover_tasks(env: "B200Env"):
+        """Task list of rai.2d_handover (rai_envs.py:502-543) with hand-placed keyframes: the
+        reference solves them with rai's KOMO at construction time (rai_config.py:844-968), which is
+        not available; these are equivalent in construction (touching pick / handover / place poses,
+        all collision free in their modes), not identical to any rai instance."""
+        k_pick1 = np.array([0.0, 0.77, 0.0])          # a1 just north of obj1 (0, .4)
+        k_hand = np.array([-1.2, 1.37, 0.0, -1.2, 0.58, 0.0])  # a1 carries obj1 to (-1.2, 1.0); a2 waits 2 cm south of it
+        k_place = np.array([1.22, 0.4, np.pi / 2])    # a2 (obj1 hanging 0.42 'north' of it) drops obj1 at (0.8, 0.4): goal1
+        k_pick2 = np.array([0.5, -1.13, 0.0])         # a1 north of obj2 (.5, -1.5)
+        k_place2 = np.array([1.3, 1.57, 0.0])         # a1 carries obj2 to (1.3, 1.2)
+        terminal = np.concatenate([env.start_pos.state()])
+        return [
+            Task("a1_pick_obj1", ["a1"], SingleGoal(k_pick1), type="pick", frames=["a1", "obj1"]),
+            Task("handover", ["a1", "a2"], GoalSet([k_hand]), type="hanover", frames=["a2", "obj1"]),
+            Task("a2_place", ["a2"], SingleGoal(k_place), type="place", frames=["table", "obj1"]),
+            Task("a1_pick_obj2", ["a1"], SingleGoal(k_pick2), type="pick", frames=["a1", "obj2"]),
+            Task("a1_place_obj2", ["a1"], SingleGoal(k_place2), type="place", frames=["table", "obj2"]),
+            Task("terminal", ["a1", "a2"], GoalSet([terminal])),
+        ]
+
+    @register("b200.2d_handover")
+    class b200_two_dim_handover(SequenceMixin, B200Env):
+        """B200 counterpart of rai.2d_handover (rai_envs.py:462-573)."""
+
+        def __init__(self, device=None):
+            mk, kw = SCENES["2d_handover"]
+            B200Env.__init__(self, mk(), kw["tol"], kw["resolution"], device=device)
+            self.manipulating_env = True
+            self.tasks = _two_dim_handover_tasks(self)
+            self.sequence = self._make_sequence_from_names(
+                ["a1_pick_obj1", "handover", "a1_pick_obj2", "a1_place_obj2", "a2_place", "terminal"])
+            BaseModeLogic.__init__(self)
+            self.prev_mode = None
+
+    def _goto_env(scene_name: str, seed: int):
+        """Geometry of a named scene with plain goto tasks: every robot moves to a sampled collision-free
+        goal, then all return home.  (The reference's pick / place keyframes come from rai's KOMO.)"""
+
+        class _Env(SequenceMixin, B200Env):
+            def __init__(self, device=None):
+                mk, kw = SCENES[scene_name]
+                B200Env.__init__(self, mk(), kw["tol"], kw["resolution"], device=device)
+                rng = np.random.RandomState(seed)
+                lim = self.limits
+                slot = self.model.slot_for(())
+                goal = None
+                for _ in range(200):
+                    cand = rng.uniform(lim[0], lim[1], (256, lim.shape[1]))
+                    ok = CudaDevice.to_numpy(self.model.check_configs(slot, cand.astype(np.float32)))
+                    if ok.any():
+                        goal = cand[int(np.argmax(ok))].astype(np.float32).astype(np.float64)
+                        break
+                if goal is None:
+                    raise RuntimeError("no collision-free goal found")
+                self.tasks = [Task(f"{r}goal", [r], SingleGoal(goal[self.robot_idx[r]])) for r in self.robots]
+                self.tasks.append(Task("terminal", list(self.robots), SingleGoal(self.start_pos.state())))
+                self.sequence = self._make_sequence_from_names([t.name for t in self.tasks])
+                BaseModeLogic.__init__(self)
+                self.prev_mode = None
+
+        _Env.__name__ = f"b200_{scene_name}_goto"
+        return _Env
+
+    b200_box_rearrangement_goto = register("b200.box_rearrangement_goto")(_goto_env("box_rearrangement", 1))
+    b200_box_stacking_goto = register("b200.box_stacking_goto")(_goto_env("box_stacking", 2))
+    b200_mobile_wall_four_goto = register("b200.mobile_wall_four_goto")(_goto_env("mobile_wall_four", 3))
+
+    # ---- abstract.test answered by the CUDA abstract kernels (bit-exact with the reference) ----
+    from multi_robot_multi_goal_planning.problems.abstract_env import (  # type: ignore
+        Rectangle, Sphere, abstract_env_two_dim_middle_obs)
+
+    class AbstractCudaDevice:
+        def __init__(self, n_agents, dim, radii, spheres, rects_minmax):
+            import torch
+            from .backend import AbstractBackend
+            self.torch = torch
+            self.be = AbstractBackend(n_agents, dim, radii, spheres, rects_minmax)
+
+        def check_configs(self, q):
+            t = self.torch
+            return self.be.check_configs(t.from_numpy(np.ascontiguousarray(q, np.float64)).cuda()).cpu().numpy()
+
+        def check_edges(self, q1, q2, resolution, N=None, n_start=0, n_max=None, include_endpoints=False):
+            t = self.torch
+            Nt = None if N is None else t.from_numpy(np.ascontiguousarray(N, np.int32)).cuda()
+            f, p = self.be.check_edges(t.from_numpy(np.ascontiguousarray(q1, np.float64)).cuda(),
+                                       t.from_numpy(np.ascontiguousarray(q2, np.float64)).cuda(), resolution, N=Nt, n_start=n_start,
+                                       n_max=n_max, include_endpoints=include_endpoints)
+            return f.cpu().numpy(), p.cpu().numpy()
+
+    @register("b200.abstract_test")
+    class b200_abstract_test(abstract_env_two_dim_middle_obs):
+        """abstract.test (abstract_env.py:381-421) with every collision query answered by the fp64 CUDA
+        kernels; flags are bit-identical, so planners behave exactly as on the reference's own env."""
+
+        def __init__(self, device=None):
+            super().__init__()
+            self._device = device
+
+        @property
+        def device(self):
+            if self._device is None:
+                sph = [(o.pos, o.radius) for o in self.obstacles if isinstance(o, Sphere)]
+                rect = [(o.min_bounds, o.max_bounds) for o in self.obstacles if isinstance(o, Rectangle)]
+                dim = len(self.start_pos[0])
+                self._device = AbstractCudaDevice(self.start_pos.num_agents(), dim, self.agent_radii, sph, rect)
+            return self._device
+
+        def is_collision_free(self, q, mode):
+            if q is None:
+                raise ValueError
+            return bool(self.device.check_configs(q.state()[None])[0])
+
+        def is_edge_collision_free(self, q1, q2, mode, resolution=None, tolerance=None, include_endpoints=False, N_start=0,
+                                   N_max=None, N=None):
+            if resolution is None:
+                resolution = self.collision_resolution
+            if N is None:
+                N = max(2, int(config_dist(q1, q2, "max") / resolution) + 1)
+            if N_start > N:
+                assert False
+            f, _ = self.device.check_edges(q1.state()[None], q2.state()[None], resolution, N=np.array([N], np.int32),
+                                           n_start=N_start, n_max=N_max, include_endpoints=include_endpoints)
+            return bool(f[0])
+
+        def batch_is_collision_free(self, qs, mode=None):
+            return self.device.check_configs(np.asarray(qs, np.float64))
+
+        def batch_is_edge_collision_free(self, q1s, q2s, mode=None, resolution=None, **kw):
+            return self.device.check_edges(np.asarray(q1s, np.float64), np.asarray(q2s, np.float64),
+                                           self.collision_resolution if resolution is None else resolution, **kw)

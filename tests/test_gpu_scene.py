@@ -134,3 +134,33 @@ def test_for_robot_rule(be):
     assert np.array_equal(got[clear], ofree[clear])
     plain = be.check_configs(slot, torch.from_numpy(q).cuda()).cpu().numpy()
     assert (got >= plain).all() and got.sum() > plain.sum()
+
+
+@pytest.mark.parametrize("name,parent,child", [("box_rearrangement", "a1_ur_vacuum", "obj11"), ("2d_handover", "a1", "obj1"),
+                                               ("mobile_wall_four", "a0_gripper", "obj_00"), ("box_stacking", "a2_ur_gripper_center", "obj00")])
+def test_held_object_modes(cuda_lib, name, parent, child):
+    """A7: kinematic tree of a mode in which a robot holds an object (attach + contact -1,
+    rai_base_env.py:776-805): the object's shapes ride on the robot link and collide with everything
+    except its parent link."""
+    from multirobot_pathplanning_benchmark_b200.env import SceneModel
+    mk, kw = SCENES[name]
+    sc = mk()
+    model = SceneModel(sc, kw["tol"], kw["resolution"])
+    rng = np.random.default_rng(3)
+    lim = sc.limits()
+    # attach at a configuration where the scene is collision free
+    base_slot = model.slot_for(())
+    cand = rng.uniform(lim[0], lim[1], (4096, sc.dof)).astype(np.float32)
+    ok = model.check_configs(base_slot, cand).cpu().numpy()
+    q_attach = cand[np.argmax(ok)].astype(np.float64)
+    slot = model.slot_for(("held",), [(parent, child, q_attach)])
+    cs = model.compiled(slot)
+    assert cs.n_moving == model.compiled(base_slot).n_moving + 1
+    q = uniform_configs(sc, 40_000, 5)
+    free, pen = model.device.be.check_configs(slot, torch.from_numpy(q).cuda(), return_penetration=True)
+    ofree, open_, omind = O.check_configs(cs.blob64, q.astype(np.float64), nthreads=O.max_threads())
+    clear = np.abs(O.margin(open_, omind, cs.tol)) > MARGIN
+    assert np.array_equal(free.cpu().numpy()[clear], ofree[clear])
+    assert np.max(np.abs(pen.cpu().numpy() - open_)) < 2e-5
+    base_free = model.check_configs(base_slot, torch.from_numpy(q).cuda()).cpu().numpy()
+    assert (free.cpu().numpy() != base_free).any()  # the mode really changes the answer
