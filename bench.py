@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:  # secondary scenes and the CPU leg are N = 1 only
+        args.no_extra = args.no_cpu = True
 
     if args.impl == "reference":
         return run_reference(args)

@@ -19,6 +19,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # --use_fast_math would also turn sincosf/sqrtf/division into approximations; the kernels ask
 # for approximate forms explicitly where they are wanted, so keep IEEE defaults elsewhere.
 NVCC_FLAGS.remove("--use_fast_math")
+if os.environ.get("MRB_DEFS"):  # experiment switches, e.g. MRB_DEFS="-DMRB_TC_E1"
+    NVCC_FLAGS += os.environ["MRB_DEFS"].split()
 
 
 def nvcc() -> str:

@@ -313,14 +313,14 @@ int mrb200_batch_dist(const double* q, const double* pts, int64_t N, int D, cons
 }
 
 // candidates kept per row by the tensor-core path
-static int tc_candidates(int k) { return k + 16; }
+static int tc_candidates(int k) { return k + 8; }
 
 static bool tc_usable(int64_t Q, int64_t N, int D, const mrb::Slices& sl, int metric, int k, mrb::TcPlan* plan) {
     if (k > 48 || N < 1024 || Q < 1) return false;
     if (!mrb::knn_tc_make_plan(D, sl, metric, plan)) return false;
-    // narrower corpus tiles until query tile + 3 corpus stages + candidate heaps fit in shared memory
-    while (plan->tn > 32 && mrb::knn_tc_smem_bytes(*plan, tc_candidates(k)) > 200 * 1024) plan->tn >>= 1;
-    return mrb::knn_tc_smem_bytes(*plan, tc_candidates(k)) <= 200 * 1024;
+    // narrower corpus tiles until query tile + corpus stages + candidate heaps fit in shared memory
+    while (plan->tn > 32 && mrb::knn_tc_smem_bytes(*plan, tc_candidates(k)) > 224 * 1024) plan->tn >>= 1;
+    return mrb::knn_tc_smem_bytes(*plan, tc_candidates(k)) <= 224 * 1024;
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -341,7 +341,7 @@ size_t mrb200_knn_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
         worst.tn = 256;
         const int64_t ct = (N + 31) / 32;  // smallest tile width -> most tiles
         tc = align256((size_t)((Q + 127) / 128) * worst.KS * 128 * 32) + align256((size_t)ct * worst.KS * 32 * 32) +
-             align256((size_t)32 * Q * tc_candidates(k) * 8) + align256((size_t)Q) + 4096;
+             align256((size_t)64 * (Q + 128) * tc_candidates(k) * 8) + align256((size_t)Q) + 4096;
     }
     return exact + tc;
 }

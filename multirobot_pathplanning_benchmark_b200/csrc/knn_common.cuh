@@ -78,14 +78,25 @@ template <typename KeyT>
 struct ThreadHeap {
     KeyT* key;
     int* idx;
-    int stride, cap, n;
+    int stride;   // element stride of the key array
+    int cap, n;
+    int istride;  // element stride of the index array (keys and indices may live in different memories)
 
-    __device__ __forceinline__ bool less(KeyT ka, int ia, KeyT kb, int ib) const { return ka < kb || (ka == kb && ia < ib); }
+    __device__ __forceinline__ ThreadHeap(KeyT* k, int* i, int stride_, int cap_, int n_ = 0, int istride_ = -1)
+        : key(k), idx(i), stride(stride_), cap(cap_), n(n_), istride(istride_ < 0 ? stride_ : istride_) {}
+
+    // (ka, idx[ia_pos]) < (kb, ib): indices are only looked at on exact key ties
+    __device__ __forceinline__ bool less_ki(KeyT ka, int ia, KeyT kb, int ib) const { return ka < kb || (ka == kb && ia < ib); }
     __device__ __forceinline__ KeyT top_key() const { return key[0]; }
     __device__ __forceinline__ int top_idx() const { return idx[0]; }
     __device__ __forceinline__ bool full() const { return n == cap; }
-    // does (k, i) belong in the heap?
-    __device__ __forceinline__ bool accepts(KeyT k, int i) const { return n < cap || less(k, i, key[0], idx[0]); }
+    __device__ __forceinline__ bool accepts(KeyT k, int i) const {
+        if (n < cap) return true;
+        const KeyT t = key[0];
+        return k < t || (k == t && i < idx[0]);
+    }
+    // entry at heap position a  <  (k, i) ?
+    __device__ __forceinline__ bool pos_less(int a, KeyT ka, KeyT k, int i) const { return ka < k || (ka == k && idx[a * istride] < i); }
 
     __device__ __forceinline__ void push(KeyT k, int i) {
         if (n < cap) {  // sift up
@@ -93,33 +104,31 @@ struct ThreadHeap {
             while (c > 0) {
                 const int p = (c - 1) >> 1;
                 const KeyT pk = key[p * stride];
-                const int pi = idx[p * stride];
-                if (!less(pk, pi, k, i)) break;
+                if (!pos_less(p, pk, k, i)) break;
                 key[c * stride] = pk;
-                idx[c * stride] = pi;
+                idx[c * istride] = idx[p * istride];
                 c = p;
             }
             key[c * stride] = k;
-            idx[c * stride] = i;
+            idx[c * istride] = i;
         } else {  // replace the maximum, sift down
             int p = 0;
             for (;;) {
                 int c = 2 * p + 1;
                 if (c >= n) break;
                 KeyT ck = key[c * stride];
-                int ci = idx[c * stride];
                 if (c + 1 < n) {
                     const KeyT ck2 = key[(c + 1) * stride];
-                    const int ci2 = idx[(c + 1) * stride];
-                    if (less(ck, ci, ck2, ci2)) { c++; ck = ck2; ci = ci2; }
+                    if (ck < ck2 || (ck == ck2 && idx[c * istride] < idx[(c + 1) * istride])) { c++; ck = ck2; }
                 }
-                if (!less(k, i, ck, ci)) break;
+                // stop when (k, i) >= child
+                if (!(k < ck || (k == ck && i < idx[c * istride]))) break;
                 key[p * stride] = ck;
-                idx[p * stride] = ci;
+                idx[p * istride] = idx[c * istride];
                 p = c;
             }
             key[p * stride] = k;
-            idx[p * stride] = i;
+            idx[p * istride] = i;
         }
     }
     // remove and return the maximum
@@ -129,25 +138,23 @@ struct ThreadHeap {
         n--;
         if (n > 0) {
             const KeyT lk = key[n * stride];
-            const int li = idx[n * stride];
+            const int li = idx[n * istride];
             int p = 0;
             for (;;) {
                 int c = 2 * p + 1;
                 if (c >= n) break;
                 KeyT ck = key[c * stride];
-                int ci = idx[c * stride];
                 if (c + 1 < n) {
                     const KeyT ck2 = key[(c + 1) * stride];
-                    const int ci2 = idx[(c + 1) * stride];
-                    if (less(ck, ci, ck2, ci2)) { c++; ck = ck2; ci = ci2; }
+                    if (ck < ck2 || (ck == ck2 && idx[c * istride] < idx[(c + 1) * istride])) { c++; ck = ck2; }
                 }
-                if (!less(lk, li, ck, ci)) break;
+                if (!(lk < ck || (lk == ck && li < idx[c * istride]))) break;
                 key[p * stride] = ck;
-                idx[p * stride] = ci;
+                idx[p * istride] = idx[c * istride];
                 p = c;
             }
             key[p * stride] = lk;
-            idx[p * stride] = li;
+            idx[p * istride] = li;
         }
     }
 };

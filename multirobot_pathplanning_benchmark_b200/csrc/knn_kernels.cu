@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(KT) knn_exact_kernel(const double* __restrict_
     double q[DMAX];
 #pragma unroll
     for (int d = 0; d < DMAX; d++) q[d] = (valid && d < D) ? queries[row * D + d] : 0.0;
-    ThreadHeap<double> heap{hk + threadIdx.x, hi + threadIdx.x, KT, k, 0};
+    ThreadHeap<double> heap(hk + threadIdx.x, hi + threadIdx.x, KT, k, 0);
     const int64_t n0 = blockIdx.y * split_len, n1 = min(N, n0 + split_len);
     stream_corpus<DMAX>(corpus, n0, n1, D, q, valid, sl, metric, tiles, bars, bulk_ok != 0, [&](double d, int idx) {
         if (heap.accepts(d, idx)) heap.push(d, idx);
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(KT) knn_merge_kernel(const double* __restrict_
     int* hi = reinterpret_cast<int*>(hk + (size_t)k * KT);
     const int64_t row = blockIdx.x * (int64_t)KT + threadIdx.x;
     if (row >= Q || (skip && skip[row])) return;
-    ThreadHeap<double> heap{hk + threadIdx.x, hi + threadIdx.x, KT, k, 0};
+    ThreadHeap<double> heap(hk + threadIdx.x, hi + threadIdx.x, KT, k, 0);
     for (int s = 0; s < splits; s++) {
         const double* pd = part_d + ((size_t)s * Q + row) * k;
         const int* pi = part_i + ((size_t)s * Q + row) * k;

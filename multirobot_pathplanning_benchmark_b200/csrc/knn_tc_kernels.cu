@@ -30,7 +30,8 @@ namespace mrb {
 
 constexpr int TC_TM = 128;        // query rows per CTA (UMMA M)
 constexpr int TC_STAGES = 3;      // shared-memory stages of corpus tiles
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;   // warps 0-3: producer / MMA / TMEM allocator / spare, warps 4-11: epilogue
+constexpr int TC_STG = 8;         // staged candidates per epilogue thread between batched heap updates
 constexpr float TC_BIG = 1.0e30f;
 
 // ---------------------------------------------------------------------------------------------
@@ -141,12 +142,6 @@ __global__ void __launch_bounds__(128) knn_tc_prep_kernel(const double* __restri
     if (real) atomicMax(max_norm_bits, __float_as_uint(worst));  // non-negative floats order like unsigned ints
 }
 
-// out of line: 32 call sites per column chunk, taken rarely
-__device__ __noinline__ float heap_insert(ThreadHeap<float>& heap, float key, int idx, float thr) {
-    if (heap.accepts(key, idx)) heap.push(key, idx);
-    return heap.full() ? heap.top_key() : thr;
-}
-
 // ---------------------------------------------------------------------------------------------
 // main kernel: grid (query tiles, corpus splits)
 // ---------------------------------------------------------------------------------------------
@@ -157,7 +152,7 @@ struct TcParams {
     int64_t tiles_per_split;  // corpus tiles per split
     int64_t n_ctiles;
     int kc;                   // candidates kept per row and split
-    float* part_key;          // [split][Q][kc]
+    float* part_key;          // [split][half][Q][kc]
     int* part_idx;
     TcPlan plan;
 };
@@ -170,9 +165,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
     const uint32_t b_bytes = (uint32_t)KS * tn * 32;
     unsigned char* sA = smem_raw;
     unsigned char* sB = sA + a_bytes;
-    float* hk = reinterpret_cast<float*>(sB + (size_t)TC_STAGES * b_bytes);   // [kc][128]
-    int* hi = reinterpret_cast<int*>(hk + (size_t)kc * TC_TM);                 // [kc][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(hi + (size_t)kc * TC_TM);
+    float* hk = reinterpret_cast<float*>(sB + (size_t)TC_STAGES * b_bytes);   // [kc][2 * 128] heaps (two column halves per row)
+    int* hi = reinterpret_cast<int*>(hk + (size_t)kc * 2 * TC_TM);             // [kc][2 * 128]
+    float* stg_k = reinterpret_cast<float*>(hi + (size_t)kc * 2 * TC_TM);      // [TC_STG][2 * 128] staged candidates
+    int* stg_i = reinterpret_cast<int*>(stg_k + (size_t)TC_STG * 2 * TC_TM);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_i + (size_t)TC_STG * 2 * TC_TM);
     uint64_t* full_b = bars;                    // [STAGES] corpus tile landed
     uint64_t* empty_b = bars + TC_STAGES;       // [STAGES] corpus tile consumed by the MMAs
     uint64_t* a_full = bars + 2 * TC_STAGES;    // query tile landed
@@ -188,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         mbar_init(a_full, 1);
-        for (int b = 0; b < 2; b++) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 4); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 8); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, alloc_cols);
@@ -244,19 +241,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = query row =====
-        const int quarter = warp & 3;
+        // ===== epilogue: 8 warps; thread = (query row, half); 32-column chunks alternate between halves =====
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
         const int r_in_tile = quarter * 32 + lane;
+        const int hslot = half * TC_TM + r_in_tile;            // this thread's heap / staging column
         const int64_t row = qtile * TC_TM + r_in_tile;
-        ThreadHeap<float> heap{hk + r_in_tile, hi + r_in_tile, TC_TM, kc, 0};
+        ThreadHeap<float> heap(hk + hslot, hi + hslot, 2 * TC_TM, kc, 0);
+        float* sk = stg_k + hslot;                             // staging [TC_STG][2 * TC_TM]
+        int* si = stg_i + hslot;
+        int staged = 0;
         float thr = 3.0e38f;
+        const int chunks_per_tile = tn >> 5;
+        // every lane pushes its staged candidates into its own heap at the same time: the sift loops of the 32
+        // lanes run side by side instead of one lane at a time
+        auto flush = [&]() {
+            for (int e = 0; e < staged; e++) {
+                const float key = sk[e * 2 * TC_TM];
+                const int idx = si[e * 2 * TC_TM];
+                if (heap.accepts(key, idx)) heap.push(key, idx);
+            }
+            staged = 0;
+            if (heap.full()) thr = heap.top_key();
+        };
         for (int64_t t = 0; t < n_tiles; ++t) {
             const int buf = (int)(t & 1);
             const uint32_t use = (uint32_t)(t >> 1);
             mbar_wait(&tm_full[buf], use & 1);
             tc_fence_after();
             const int64_t col0 = (t0 + t) * tn;
-            for (int c = 0; c < tn; c += 32) {
+            for (int ci = 0; ci < chunks_per_tile; ci++) {
+                if (((t * chunks_per_tile + ci) & 1) != half) continue;   // warp-uniform
+                const int c = ci << 5;
                 float v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * buf_cols + c);
                 tmem_ld32(taddr, v);
@@ -268,27 +283,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], u[j]);
                 }
-                float m = v[0];
+                uint32_t mask = 0u;
 #pragma unroll
-                for (int j = 1; j < 32; j++) m = fminf(m, v[j]);
-                if (m < thr) {
+                for (int j = 0; j < 32; j++) mask |= (v[j] < thr ? 1u : 0u) << j;
+                while (mask) {  // a handful of candidates per chunk and warp
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    // v[j] with a run-time j: five levels of selects keep v in registers
+                    float s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int64_t col = col0 + c + j;
-                        if (v[j] < thr && col < p.N) thr = heap_insert(heap, v[j], (int)col, thr);
+                    for (int i = 0; i < 16; i++) s16[i] = (j & 16) ? v[16 + i] : v[i];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) s8[i] = (j & 8) ? s16[8 + i] : s16[i];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) s4[i] = (j & 4) ? s8[4 + i] : s8[i];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) s2[i] = (j & 2) ? s4[2 + i] : s4[i];
+                    const float val = (j & 1) ? s2[1] : s2[0];
+                    const int64_t col = col0 + c + j;
+                    if (col < p.N) {
+                        if (staged == TC_STG) flush();  // only while the heap is still filling up
+                        sk[staged * 2 * TC_TM] = val;
+                        si[staged * 2 * TC_TM] = (int)col;
+                        staged++;
                     }
                 }
+                if (__any_sync(0xffffffffu, staged >= TC_STG - 2)) flush();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tm_empty[buf]);
         }
+        flush();
         if (row < p.Q) {
-            float* ok = p.part_key + ((size_t)blockIdx.y * p.Q + row) * kc;
-            int* oi = p.part_idx + ((size_t)blockIdx.y * p.Q + row) * kc;
+            float* ok = p.part_key + (((size_t)blockIdx.y * 2 + half) * p.Q + row) * kc;
+            int* oi = p.part_idx + (((size_t)blockIdx.y * 2 + half) * p.Q + row) * kc;
             for (int e = 0; e < kc; e++) {
-                ok[e] = e < heap.n ? heap.key[e * TC_TM] : 3.0e38f;
-                oi[e] = e < heap.n ? heap.idx[e * TC_TM] : -1;
+                ok[e] = e < heap.n ? heap.key[e * 2 * TC_TM] : 3.0e38f;
+                oi[e] = e < heap.n ? heap.idx[e * 2 * TC_TM] : -1;
             }
         }
     }
@@ -306,15 +338,15 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const double* __restric
                                                          int splits, const float* __restrict__ part_key, const int* __restrict__ part_idx,
                                                          const unsigned* __restrict__ max_norm_bits, int32_t* __restrict__ out_idx,
                                                          double* __restrict__ out_dist, uint8_t* __restrict__ certified) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* hk = reinterpret_cast<double*>(smem_raw);
+    extern __shared__ __align__(16) unsigned char smem_rr[];
+    double* hk = reinterpret_cast<double*>(smem_rr);
     int* hi = reinterpret_cast<int*>(hk + (size_t)k * 128);
     const int64_t row = blockIdx.x * (int64_t)128 + threadIdx.x;
     if (row >= Q) return;
     double q[DMAX];
 #pragma unroll
     for (int d = 0; d < DMAX; d++) q[d] = d < D ? queries[row * D + d] : 0.0;
-    ThreadHeap<double> heap{hk + threadIdx.x, hi + threadIdx.x, 128, k, 0};
+    ThreadHeap<double> heap(hk + threadIdx.x, hi + threadIdx.x, 128, k, 0);
     float tau = 3.0e38f;  // smallest coarse value any discarded point can have
     for (int s = 0; s < splits; s++) {
         const float* pk = part_key + ((size_t)s * Q + row) * kc;
@@ -384,7 +416,7 @@ bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan) {
 }
 
 size_t knn_tc_smem_bytes(const TcPlan& plan, int kc) {
-    return (size_t)plan.KS * TC_TM * 32 + (size_t)TC_STAGES * plan.KS * plan.tn * 32 + (size_t)kc * TC_TM * 8 + 16 * 8 + 1024;
+    return (size_t)plan.KS * TC_TM * 32 + (size_t)TC_STAGES * plan.KS * plan.tn * 32 + (size_t)(kc + TC_STG) * 2 * TC_TM * 8 + 16 * 8 + 1024;
 }
 
 int knn_tc_splits(int64_t Q, int64_t n_ctiles) {
@@ -402,7 +434,7 @@ int knn_tc_splits(int64_t Q, int64_t n_ctiles) {
 
 size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, int splits) {
     const int64_t qt = (Q + TC_TM - 1) / TC_TM, ct = (N + plan.tn - 1) / plan.tn;
-    return (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)splits * Q * kc * 8 + (size_t)Q + 1024;
+    return (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)splits * 2 * Q * kc * 8 + (size_t)Q + 1024;
 }
 
 cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
@@ -417,7 +449,7 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     float* B = (float*)w;
     w += (size_t)ct * plan.KS * plan.tn * 32;
     float* part_key = (float*)w;
-    w += (size_t)splits * Q * kc * 4;
+    w += (size_t)splits * 2 * Q * kc * 4;
     int* part_idx = (int*)w;
     cudaError_t e = cudaMemsetAsync(max_norm, 0, 4, st);
     if (e != cudaSuccess) return e;
@@ -445,7 +477,7 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     do {                                                                                                                          \
         e = cudaFuncSetAttribute(knn_rerank_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);                 \
         if (e != cudaSuccess) return e;                                                                                           \
-        knn_rerank_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, rsmem, st>>>(queries, corpus, Q, D, sl, metric, k, kc, splits,  \
+        knn_rerank_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, rsmem, st>>>(queries, corpus, Q, D, sl, metric, k, kc, 2 * splits,  \
                                                                                part_key, part_idx, max_norm, out_idx, out_dist,  \
                                                                                certified);                                        \
     } while (0)

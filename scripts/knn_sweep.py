@@ -1,0 +1,13 @@
+import sys, numpy as np, torch
+sys.path.insert(0, ".")
+from multirobot_pathplanning_benchmark_b200 import knn as K
+N = 100000
+c = torch.from_numpy(np.random.RandomState(5).uniform(-3.2, 3.2, (N, 24))).cuda()
+for R in (1, 2, 3, 4, 6, 8):
+    d = 24 // R
+    sl = [[r * d, (r + 1) * d] for r in range(R)]
+    K.batch_knn(c[:4096], c, sl, "max_euclidean", 33, mode="tensor")
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); K.batch_knn(c, c, sl, "max_euclidean", 33, mode="tensor"); b.record(); b.synchronize()
+    print("R", R, "%.2f ms" % a.elapsed_time(b))
