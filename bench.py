@@ -360,6 +360,23 @@ def main():
             knn_res["cpu_port_queries_per_s_1core"] = nq / (time.perf_counter() - t)
         extra["knn_box_stacking_100k"] = knn_res
         del corpus
+        # time-to-first-solution of the batch-native PRM (planner.py): same planner code, same seeds, B200 backend
+        # vs the CPU oracle backend answering the same batch calls (BASELINE.md plan item 4)
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import ttfs
+        ttfs.run("2d_handover", "b200", 99, 200, 30, 30)   # warm-up
+        tt = {}
+        for sname, n0, t0, cpu_seeds in (("2d_handover", 500, 60, 3), ("box_rearrangement", 4000, 400, 1), ("box_stacking", 6000, 600, 1)):
+            gpu_runs = [ttfs.run(sname, "b200", seed, n0, t0, 120) for seed in range(3)]
+            entry = {"samples_per_mode": n0, "b200_median_s": float(np.median([r["time_s"] for r in gpu_runs])),
+                     "b200_runs": gpu_runs}
+            if not args.no_cpu:
+                cpu_runs = [ttfs.run(sname, "cpu", seed, n0, t0, 240) for seed in range(cpu_seeds)]
+                entry["cpu_port_median_s"] = float(np.median([r["time_s"] for r in cpu_runs]))
+                entry["cpu_runs"] = cpu_runs
+                entry["same_plans"] = all(abs(a["cost"] - b["cost"]) < 1e-9 for a, b in zip(gpu_runs, cpu_runs))
+            tt[sname] = entry
+        extra["prm_time_to_first_solution"] = tt
     else:
         edge_inputs = None
 
