@@ -330,24 +330,27 @@ __device__ __forceinline__ float narrow_pair(const TileCtx& c, int a, int b, int
     }
 }
 
+// queue entry: bits 0..4 configuration, bits 5..28 record index inside its sublist, bits 29..30 sublist
 template <int T>
-__device__ __noinline__ void drain(const TileCtx& c, int off_ids, uint32_t entry, bool valid) {
+__device__ __noinline__ void drain(const TileCtx& c, uint32_t entry, bool valid) {
     if (valid) {
         const int cfg = entry & 31;
-        const uint32_t pk = c.bi[off_ids + (entry >> 5)];
+        const int hdr = MRB_H_BP + (T * MRB_BP_SUBLISTS + (int)(entry >> 29)) * 2;
+        // a sublist's n records (2 words each) are followed by its n packed pair ids
+        const uint32_t pk = c.bi[c.bi[hdr] + 2 * c.bi[hdr + 1] + ((entry >> 5) & 0xffffffu)];
         const int a = pk & 0xffff, b = (pk >> 16) & 0xfff;
         c.add_pen(cfg, a, b, narrow_pair<T>(c, a, b, cfg));
     }
 }
 
-__device__ __noinline__ void drain_any(const TileCtx& c, int type, int off_ids, uint32_t entry, bool valid) {
+__device__ __noinline__ void drain_any(const TileCtx& c, int type, uint32_t entry, bool valid) {
     switch (type) {  // warp-uniform
-        case MRB_PT_SEG_SEG: drain<MRB_PT_SEG_SEG>(c, off_ids, entry, valid); break;
-        case MRB_PT_SEG_BOX: drain<MRB_PT_SEG_BOX>(c, off_ids, entry, valid); break;
-        case MRB_PT_POINT_POINT: drain<MRB_PT_POINT_POINT>(c, off_ids, entry, valid); break;
-        case MRB_PT_POINT_SEG: drain<MRB_PT_POINT_SEG>(c, off_ids, entry, valid); break;
-        case MRB_PT_POINT_BOX: drain<MRB_PT_POINT_BOX>(c, off_ids, entry, valid); break;
-        default: drain<MRB_PT_BOX_BOX>(c, off_ids, entry, valid); break;
+        case MRB_PT_SEG_SEG: drain<MRB_PT_SEG_SEG>(c, entry, valid); break;
+        case MRB_PT_SEG_BOX: drain<MRB_PT_SEG_BOX>(c, entry, valid); break;
+        case MRB_PT_POINT_POINT: drain<MRB_PT_POINT_POINT>(c, entry, valid); break;
+        case MRB_PT_POINT_SEG: drain<MRB_PT_POINT_SEG>(c, entry, valid); break;
+        case MRB_PT_POINT_BOX: drain<MRB_PT_POINT_BOX>(c, entry, valid); break;
+        default: drain<MRB_PT_BOX_BOX>(c, entry, valid); break;
     }
 }
 
@@ -356,8 +359,8 @@ __device__ __noinline__ void drain_any(const TileCtx& c, int type, int off_ids, 
 // per set bit, and drains 32 entries at a time through the exact narrowphase.
 struct Survivors {
     const TileCtx& c;
-    int type, off_ids, qn;
-    __device__ __forceinline__ void flush(uint32_t mask, int first_record) {
+    int type, qn;
+    __device__ __forceinline__ void flush(uint32_t mask, int first_record, int sub) {
         const unsigned lt = (1u << c.lane) - 1u;
         for (;;) {
             const unsigned m = __ballot_sync(FULL, mask != 0u);
@@ -365,7 +368,7 @@ struct Survivors {
             if (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1u;
-                c.queue[qn + __popc(m & lt)] = ((uint32_t)(first_record + j) << 5) | (uint32_t)c.lane;
+                c.queue[qn + __popc(m & lt)] = ((uint32_t)sub << 29) | ((uint32_t)(first_record + j) << 5) | (uint32_t)c.lane;
             }
             qn += __popc(m);
             __syncwarp();
@@ -376,14 +379,14 @@ struct Survivors {
                 qn -= TILE;
                 if (c.lane < qn) c.queue[c.lane] = tail;
                 __syncwarp();
-                drain_any(c, type, off_ids, entry, true);
+                drain_any(c, type, entry, true);
             }
         }
     }
     __device__ __forceinline__ void finish() {
         if (qn > 0) {
             const uint32_t entry = c.queue[c.lane];
-            drain_any(c, type, off_ids, entry, c.lane < qn);
+            drain_any(c, type, entry, c.lane < qn);
         }
         qn = 0;
         __syncwarp();
@@ -399,12 +402,12 @@ __device__ __noinline__ void run_queued_types(const TileCtx& c, int warp, bool s
     const char* Wl = reinterpret_cast<const char*>(c.W + lane);  // this lane's column of W
     const float4* scentre = reinterpret_cast<const float4*>(bf + bi[MRB_H_OFF_SCENTRE]);
     for (int type = 0; type <= MRB_PT_BOX_BOX; ++type) {
+        Survivors sv{c, type, 0};  // one queue per pair type: partial batches only at the end of a type
         for (int sub = 0; sub < MRB_BP_SUBLISTS; ++sub) {
             const int n = bi[MRB_H_BP + (type * MRB_BP_SUBLISTS + sub) * 2 + 1];
             if (n == 0) continue;
             const int off = bi[MRB_H_BP + (type * MRB_BP_SUBLISTS + sub) * 2];
             const int lo = (n * warp) / WARPS, hi = (n * (warp + 1)) / WARPS;
-            Survivors sv{c, type, off + 2 * n, 0};
             const uint2* rec = reinterpret_cast<const uint2*>(bi + off);
             const bool seg_x = type == MRB_PT_SEG_BOX;
             unsigned prev_x = 0xffffffffu;
@@ -458,10 +461,10 @@ __device__ __noinline__ void run_queued_types(const TileCtx& c, int warp, bool s
                     }
                 }
                 if (skip_decided && c.pen_fx[lane] > tol_fx) mask = 0u;
-                sv.flush(mask, base);
+                sv.flush(mask, base, sub);
             }
-            sv.finish();
         }
+        sv.finish();
     }
 }
 
