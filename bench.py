@@ -294,7 +294,12 @@ def main():
     bytes_cfg = 4 * D + 1
     roofline = {
         "bound": "fp32_simt", "kernel": "check_configs_kernel", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp32_peak, "traffic": None,
+        "frac": achieved / fp32_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, from the committed
+        # `ncu --set full` capture (profiles/r1_check_configs_v2_broadphase.txt): 203.5 MB + 17.7 MB
+        "traffic": 221.2e6 if args.workload == DEFAULT else None,
+        "algorithmic_bytes": (4 * D + 1) * B,
+        "bound_note": "FK + narrowphase is FP32-FMA bound (SURVEY.md 8d); the HBM view is reported under 'hbm'",
         "peak_source": "measured live by mrb200_fp32_probe (MEASURED_PEAKS.json has no FP32-SIMT figure)",
         "algorithmic_flop_per_config": flop_cfg, "kernel_ms": kernel_ms,
         "hbm": {"achieved": bytes_cfg * B / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
