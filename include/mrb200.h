@@ -105,6 +105,12 @@ int mrb200_scene_info(const mrb200_scene_t* scene, int slot, int32_t* out4);
 int mrb200_batch_dist(const double* q_dev /*[D]*/, const double* pts_dev /*[N, D]*/, int64_t N, int D,
                       const int32_t* slices_host, int R, int metric, double* out_dev /*[N]*/,
                       mrb200_stream_t stream);
+/* batch_config_cost (P/problems/core/configuration.py:437-510): out[n] = cost(a[n] or the single row a, b[n]);
+ * per-robot metric euclidean (per_robot_max = 0) or max-abs (1); reduction max + w * sum (reduction_sum = 0,
+ * the reference's "max" with w = 0.01) or sum (1). */
+int mrb200_batch_cost(const double* a_dev, int a_is_single, const double* b_dev /*[N, D]*/, int64_t N, int D,
+                      const int32_t* slices_host, int R, int per_robot_max, int reduction_sum, double w,
+                      double* out_dev /*[N]*/, mrb200_stream_t stream);
 /* k nearest neighbours of every query row, ascending (distance, index); rows with fewer than k
  * corpus points are padded with index -1 / distance +inf.  out_dist_dev nullable.  The workspace
  * (device, mrb200_knn_workspace_bytes) is scratch for partial results.

@@ -325,6 +325,19 @@ static bool tc_usable(int64_t Q, int64_t N, int D, const mrb::Slices& sl, int me
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+int mrb200_batch_cost(const double* a, int a_is_single, const double* b, int64_t N, int D, const int32_t* slices_host, int R,
+                      int per_robot_max, int reduction_sum, double w, double* out_dev, mrb200_stream_t stream) {
+    mrb::Slices sl;
+    if (int rc = make_slices(slices_host, R, D, MRB200_METRIC_MAX_EUCLIDEAN, &sl)) return rc;
+    if (N < 0 || (N && (!a || !b || !out_dev))) return fail(MRB200_ERR_ARG, "batch_cost: bad argument");
+    if (N == 0) return MRB200_OK;
+    cudaError_t e = mrb::launch_batch_cost(a, a_is_single ? 0 : D, b, N, D, sl, per_robot_max, reduction_sum, w, out_dev,
+                                           (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "batch_cost");
+    g_launches++;
+    return MRB200_OK;
+}
+
 size_t mrb200_knn_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
     if (Q <= 0 || k <= 0) return 256;
     const int splits = mrb::knn_pick_splits(Q, N);

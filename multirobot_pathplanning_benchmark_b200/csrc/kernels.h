@@ -71,6 +71,8 @@ cudaError_t launch_batch_dist(const double* q, const double* pts, int64_t N, int
 cudaError_t launch_knn_exact(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
                              int k, int splits, double* part_d, int* part_i, int32_t* out_idx, double* out_dist, const uint8_t* skip,
                              cudaStream_t st);
+cudaError_t launch_batch_cost(const double* a, int64_t a_stride, const double* b, int64_t N, int D, const Slices& sl, int per_robot_max,
+                              int reduction_sum, double w, double* out, cudaStream_t st);
 // tensor-core candidate generator + exact re-rank (knn_tc_kernels.cu)
 struct TcPlan;
 bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan);

@@ -40,6 +40,45 @@ __global__ void __launch_bounds__(256) batch_dist_kernel(const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// batch_config_cost (A11): per-robot euclidean or max-abs distance, reduced by sum or by
+// max + w * sum (P/problems/core/configuration.py:156-171, 491-510).  a: one row (stride 0) or N rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) batch_cost_kernel(const double* __restrict__ a, int64_t a_stride, const double* __restrict__ b,
+                                                         int64_t N, int D, const __grid_constant__ Slices sl, int per_robot_max,
+                                                         int reduction_sum, double w, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* pa = a + i * a_stride;
+        const double* pb = b + i * D;
+        double mx = 0.0, sum = 0.0;
+        for (int r = 0; r < sl.R; r++) {
+            double d = 0.0;
+            if (per_robot_max) {
+                for (int k = sl.start[r]; k < sl.end[r]; k++) d = fmax(d, fabs(__dsub_rn(pa[k], pb[k])));
+            } else {
+                double s = 0.0;
+                for (int k = sl.start[r]; k < sl.end[r]; k++) {
+                    const double x = __dsub_rn(pa[k], pb[k]);
+                    s = __dadd_rn(s, __dmul_rn(x, x));
+                }
+                d = __dsqrt_rn(s);
+            }
+            mx = r == 0 ? d : fmax(mx, d);
+            sum = r == 0 ? d : __dadd_rn(sum, d);
+        }
+        out[i] = reduction_sum ? sum : __dadd_rn(mx, __dmul_rn(w, sum));
+    }
+}
+
+cudaError_t launch_batch_cost(const double* a, int64_t a_stride, const double* b, int64_t N, int D, const Slices& sl, int per_robot_max,
+                              int reduction_sum, double w, double* out, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    int64_t blocks = (N + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    batch_cost_kernel<<<(int)blocks, 256, 0, st>>>(a, a_stride, b, N, D, sl, per_robot_max, reduction_sum, w, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // corpus streaming: calls sink(dist, index) for every corpus point in [n0, n1), ascending
 // ---------------------------------------------------------------------------------------------
 template <int DMAX, typename Sink>

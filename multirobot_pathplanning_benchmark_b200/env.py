@@ -292,6 +292,55 @@ if HAVE_REFERENCE:
                 N=np.array([N], np.int32), n_start=N_start, n_max=N_max, include_endpoints=include_endpoints, tol=tolerance)
             return bool(CudaDevice.to_numpy(free)[0])
 
+        def is_path_collision_free(self, path, binary_order: bool = True, resolution=None, tolerance=None,
+                                   check_edges_in_order: bool = False, check_start_and_end: bool = True) -> bool:
+            """Same answer as BaseProblem.is_path_collision_free (planning_env.py:1765-1881) -- every vertex and
+            the interior of every edge collision free -- from one vertex batch and one edge batch per mode."""
+            if resolution is None:
+                resolution = self.collision_resolution
+            L = len(path)
+            by_mode: Dict[int, list] = {}
+            for i, st in enumerate(path):
+                by_mode.setdefault(id(st.mode), [st.mode, [], []])
+                if check_start_and_end or 0 < i < L - 1 or (i == L - 1 and not check_edges_in_order and False):
+                    by_mode[id(st.mode)][1].append(i)
+                if i + 1 < L:
+                    by_mode[id(st.mode)][2].append(i)
+            for mode, verts, edges in by_mode.values():
+                self.set_to_mode(mode)
+                if verts:
+                    q = np.stack([np.asarray(path[i].q.state(), np.float32) for i in verts])
+                    if not bool(CudaDevice.to_numpy(self.model.device.check_configs(self._slot, q, tolerance)).all()):
+                        return False
+                if edges:
+                    q1 = np.stack([np.asarray(path[i].q.state(), np.float32) for i in edges])
+                    q2 = np.stack([np.asarray(path[i + 1].q.state(), np.float32) for i in edges])
+                    N = np.array([max(2, int(config_dist(path[i].q, path[i + 1].q, "max") / resolution) + 1) for i in edges], np.int32)
+                    free, _ = self.model.device.check_edges(self._slot, q1, q2, resolution, N=N, tol=tolerance)
+                    if not bool(CudaDevice.to_numpy(free).all()):
+                        return False
+            return True
+
+        def sample_valid_uniform_batch(self, mode, n: int, rng: Optional[np.random.RandomState] = None, max_rounds: int = 64):
+            """Rejection sampling of n collision-free configurations in `mode`, whole batches at a time
+            (the batch form of JointRejectionSampler, P/planners/collision_free_sampler.py:106-112)."""
+            rng = rng or np.random
+            self.set_to_mode(mode)
+            out, have = [], 0
+            batch = max(256, 2 * n)
+            for _ in range(max_rounds):
+                q = rng.uniform(self.limits[0], self.limits[1], (batch, self.limits.shape[1])).astype(np.float32)
+                ok = CudaDevice.to_numpy(self.model.device.check_configs(self._slot, q)).astype(bool)
+                out.append(q[ok].astype(np.float64))
+                have += int(ok.sum())
+                if have >= n:
+                    break
+                batch *= 2
+            res = np.concatenate(out)[:n]
+            if len(res) < n:
+                raise RuntimeError("could not find enough collision-free configurations")
+            return res
+
         # ---- additive batch variants (arrays or CUDA tensors in, device tensors out) -----------
         def batch_is_collision_free(self, qs, mode):
             self.set_to_mode(mode)

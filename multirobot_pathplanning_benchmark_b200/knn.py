@@ -53,6 +53,26 @@ def batch_config_dist(q: torch.Tensor, pts: torch.Tensor, slices=None, metric: s
     return out
 
 
+def batch_config_cost(a: torch.Tensor, b: torch.Tensor, slices, metric: str = "euclidean", reduction: str = "max",
+                      w: float = 0.01) -> torch.Tensor:
+    """Cost between configuration(s) a ([D] or [N, D]) and rows of b [N, D] (configuration.py:437-510):
+    per-robot `metric` in {"euclidean", "max"}, reduced by "max" (= max + w * sum) or "sum"."""
+    lib = _lib.load()
+    b = _f64(b, "b")
+    a = _f64(a, "a")
+    N, D = b.shape
+    single = a.dim() == 1
+    if (single and a.numel() != D) or (not single and a.shape != b.shape):
+        raise ValueError("shape mismatch")
+    s, R = _slices(slices)
+    out = torch.empty(N, dtype=torch.float64, device=b.device)
+    with torch.cuda.device(b.device):
+        _lib.check(lib.mrb200_batch_cost(a.data_ptr(), int(single), b.data_ptr(), N, D, s.ctypes.data_as(_lib.c_i32p), R,
+                                         int(metric != "euclidean"), int(reduction == "sum"), float(w), out.data_ptr(),
+                                         _stream(b.device)), "batch_cost")
+    return out
+
+
 def prm_k_star(N: int, D: int) -> int:
     """k* = int(e (1 + 1/D) ln N) + 1, clipped to N (prm_graph.py:440-445)."""
     return min(int(math.e * (1 + 1 / D) * math.log(N)) + 1, N) if N > 0 else 0

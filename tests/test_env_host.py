@@ -114,3 +114,21 @@ def test_planners_behave_identically_on_b200_abstract_test(reference, envmod, pl
     assert p_ref is not None and p_b is not None and len(p_ref) == len(p_b)
     for a, b in zip(p_ref, p_b):
         assert np.array_equal(a.q.state(), b.q.state()) and a.mode.task_ids == b.mode.task_ids
+
+
+def test_batched_path_check_equals_reference_path_check(reference, envmod):
+    from multi_robot_multi_goal_planning.problems.planning_env import BaseProblem, State
+    env = envmod.b200_two_dim_handover(device=OracleSceneDevice())
+    rng = np.random.RandomState(0)
+    modes = walk_modes(env)
+    agree = 0
+    for trial in range(30):
+        m, q0 = modes[trial % len(modes)]
+        pts = [q0.state()] + [q0.state() + rng.uniform(-0.25, 0.25, 6) for _ in range(3)]
+        path = [State(env.start_pos.from_flat(p), m) for p in pts]
+        want = BaseProblem.is_path_collision_free(env, path)   # the reference's own loop over single queries
+        assert env.is_path_collision_free(path) == want
+        agree += want
+    assert 0 < agree < 30
+    qs = env.sample_valid_uniform_batch(env.start_mode, 100, np.random.RandomState(1))
+    assert qs.shape == (100, 6) and all(env.is_collision_free(env.start_pos.from_flat(q), env.start_mode) for q in qs[:10])

@@ -124,3 +124,17 @@ def test_tensor_core_path_with_duplicates_falls_back_exactly(knn):
     i_e, d_e = knn.batch_knn(q, c, sl, "max_euclidean", 30, mode="exact")
     assert torch.equal(i_t, i_e) and torch.equal(d_t, d_e)
     assert (d_t == 0).all()
+
+
+@pytest.mark.parametrize("name", ["d22", "d77", "d333", "d25", "d14", "d6666"])
+def test_batch_cost_matches_reference_golden(knn, golden, name):
+    q, pts, sl = golden[f"met_{name}_q"], golden[f"met_{name}_pts"], golden[f"met_{name}_slices"]
+    for metric in ("euclidean", "max"):
+        for red in ("max", "sum"):
+            got = knn.batch_config_cost(torch.from_numpy(q).cuda(), torch.from_numpy(pts).cuda(), sl, metric, red).cpu().numpy()
+            assert np.allclose(got, golden[f"met_{name}_cost_{metric}_{red}"], rtol=1e-15, atol=0)
+            assert np.array_equal(got, OA.batch_config_cost(q[None, :] - pts, sl, metric, red))
+    # pairwise form
+    a = pts[::-1].copy()
+    got = knn.batch_config_cost(torch.from_numpy(a).cuda(), torch.from_numpy(pts).cuda(), sl).cpu().numpy()
+    assert np.array_equal(got, OA.batch_config_cost(a - pts, sl, "euclidean", "max"))
