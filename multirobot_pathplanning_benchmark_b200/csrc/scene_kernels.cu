@@ -551,7 +551,7 @@ __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob
 // configuration batch kernel (A5 / A6 batch variant)
 // ------------------------------------------------------------------------------------------
 template <int WARPS>
-__global__ void __launch_bounds__(TILE * WARPS, 20 / WARPS) check_configs_kernel(ConfigParams p) {
+__global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel(ConfigParams p) {
     constexpr int THREADS = TILE * WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(TILE * WARPS, 20 / WARPS) check_configs_kernel
 // per step in the reference's binary order, early exit on the first colliding step
 // ------------------------------------------------------------------------------------------
 template <int WARPS>
-__global__ void __launch_bounds__(TILE * WARPS, 20 / WARPS) check_edges_kernel(EdgeParams p) {
+__global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(EdgeParams p) {
     constexpr int THREADS = TILE * WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
