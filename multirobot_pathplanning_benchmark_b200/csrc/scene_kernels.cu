@@ -332,7 +332,7 @@ __device__ __forceinline__ float narrow_pair(const TileCtx& c, int a, int b, int
 
 // queue entry: bits 0..4 configuration, bits 5..28 record index inside its sublist, bits 29..30 sublist
 template <int T>
-__device__ __noinline__ void drain(const TileCtx& c, uint32_t entry, bool valid) {
+__device__ __noinline__ void drain(const TileCtx c, uint32_t entry, bool valid) {  // by value: keeps the context in registers
     if (valid) {
         const int cfg = entry & 31;
         const int hdr = MRB_H_BP + (T * MRB_BP_SUBLISTS + (int)(entry >> 29)) * 2;
@@ -343,7 +343,7 @@ __device__ __noinline__ void drain(const TileCtx& c, uint32_t entry, bool valid)
     }
 }
 
-__device__ __noinline__ void drain_any(const TileCtx& c, int type, uint32_t entry, bool valid) {
+__device__ __noinline__ void drain_any(const TileCtx c, int type, uint32_t entry, bool valid) {
     switch (type) {  // warp-uniform
         case MRB_PT_SEG_SEG: drain<MRB_PT_SEG_SEG>(c, entry, valid); break;
         case MRB_PT_SEG_BOX: drain<MRB_PT_SEG_BOX>(c, entry, valid); break;
@@ -358,7 +358,7 @@ __device__ __noinline__ void drain_any(const TileCtx& c, int type, uint32_t entr
 // <= 32 records passed in a bit mask; flush() turns the masks into queue entries, one round
 // per set bit, and drains 32 entries at a time through the exact narrowphase.
 struct Survivors {
-    const TileCtx& c;
+    const TileCtx c;  // a copy: a reference would force the context into local memory
     int type, qn;
     __device__ __forceinline__ void flush(uint32_t mask, int first_record, int sub) {
         const unsigned lt = (1u << c.lane) - 1u;
@@ -395,7 +395,7 @@ struct Survivors {
 
 // One routine for every queued pair type: the broadphase only needs the records.
 template <int WARPS>
-__device__ __noinline__ void run_queued_types(const TileCtx& c, int warp, bool skip_decided, unsigned tol_fx) {
+__device__ __noinline__ void run_queued_types(const TileCtx c, int warp, bool skip_decided, unsigned tol_fx) {
     const uint32_t* bi = c.bi;
     const float* bf = c.bf;
     const int lane = c.lane;
@@ -415,30 +415,22 @@ __device__ __noinline__ void run_queued_types(const TileCtx& c, int warp, bool s
             for (int base = lo; base < hi; base += 32) {
                 const int cnt = min(32, hi - base);
                 uint32_t mask = 0u;
-                if (sub == 0) {  // partner moving: bounding spheres
+                if (sub == 0) {  // partner moving: bounding spheres (branch-free body: independent iterations overlap)
+#pragma unroll 4
                     for (int j = 0; j < cnt; ++j) {
                         const uint2 r = rec[base + j];
-                        const unsigned xo = r.x & 0xffffu;
-                        if (xo != prev_x) {  // warp-uniform: records are sorted by X
-                            const float* px = reinterpret_cast<const float*>(Wl + xo);
-                            cx = px[0]; cy = px[TILE]; cz = px[2 * TILE];
-                            prev_x = xo;
-                        }
+                        const float* px = reinterpret_cast<const float*>(Wl + (r.x & 0xffffu));
                         const float* py = reinterpret_cast<const float*>(Wl + (r.x >> 16));
-                        const float x = cx - py[0], y = cy - py[TILE], z = cz - py[2 * TILE];
+                        const float x = px[0] - py[0], y = px[TILE] - py[TILE], z = px[2 * TILE] - py[2 * TILE];
                         mask |= (dot3(x, y, z, x, y, z) < __uint_as_float(r.y) ? 1u : 0u) << j;
                     }
                 } else if (sub == 1) {  // partner static: bounding spheres
+#pragma unroll 4
                     for (int j = 0; j < cnt; ++j) {
                         const uint2 r = rec[base + j];
-                        const unsigned xo = r.x & 0xffffu;
-                        if (xo != prev_x) {
-                            const float* px = reinterpret_cast<const float*>(Wl + xo);
-                            cx = px[0]; cy = px[TILE]; cz = px[2 * TILE];
-                            prev_x = xo;
-                        }
+                        const float* px = reinterpret_cast<const float*>(Wl + (r.x & 0xffffu));
                         const float4 cb = scentre[r.x >> 16];
-                        const float x = cx - cb.x, y = cy - cb.y, z = cz - cb.z;
+                        const float x = px[0] - cb.x, y = px[TILE] - cb.y, z = px[2 * TILE] - cb.z;
                         mask |= (dot3(x, y, z, x, y, z) < __uint_as_float(r.y) ? 1u : 0u) << j;
                     }
                 } else {  // partner is a large static box: separating-axis bound along its face normals
