@@ -149,20 +149,25 @@ __device__ __forceinline__ float d_seg_box(const float* seg, const float* c, con
     return f > 0.f ? sqrtf(f) - rsum : -rsum;
 }
 
-// 15-axis separating-axis test: max over axes of the gap (<= 0: cores overlap)
-__device__ __forceinline__ float box_box_sat(const float* cA, const float* RA, const float* hA, const float* cB,
-                                             const float* RB, const float* hB) {
-    float R[3][3], AR[3][3], t[3];
-    float twx = cB[0] - cA[0], twy = cB[1] - cA[1], twz = cB[2] - cA[2];
+// relative pose of box B in the frame of box A: R[i][j] = a_i . b_j, t = RA^T (cB - cA)
+__device__ __forceinline__ void box_box_rel(const float* cA, const float* RA, const float* cB, const float* RB,
+                                            float (&R)[3][3], float (&t)[3]) {
+    const float twx = cB[0] - cA[0], twy = cB[1] - cA[1], twz = cB[2] - cA[2];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         t[i] = dot3(RA[i], RA[3 + i], RA[6 + i], twx, twy, twz);
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            R[i][j] = dot3(RA[i], RA[3 + i], RA[6 + i], RB[j], RB[3 + j], RB[6 + j]);
-            AR[i][j] = fabsf(R[i][j]);
-        }
+        for (int j = 0; j < 3; j++) R[i][j] = dot3(RA[i], RA[3 + i], RA[6 + i], RB[j], RB[3 + j], RB[6 + j]);
     }
+}
+
+// 15-axis separating-axis test: max over axes of the gap (<= 0: cores overlap)
+__device__ __forceinline__ float box_box_sat(const float (&R)[3][3], const float (&t)[3], const float* hA, const float* hB) {
+    float AR[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) AR[i][j] = fabsf(R[i][j]);
     float s = -3.0e38f;
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -189,42 +194,61 @@ __device__ __forceinline__ float box_box_sat(const float* cA, const float* RA, c
     return s;
 }
 
-__device__ __forceinline__ void box_edge(const float* c, const float* R, const float* h, int e, float* seg) {
-    int ax = e >> 2, u = (ax + 1) % 3, v = (ax + 2) % 3;
-    float su = (e & 1) ? h[u] : -h[u], sv = (e & 2) ? h[v] : -h[v];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        float base = fmaf(su, R[k * 3 + u], fmaf(sv, R[k * 3 + v], c[k]));
-        seg[k] = fmaf(-h[ax], R[k * 3 + ax], base);
-        seg[3 + k] = fmaf(h[ax], R[k * 3 + ax], base);
-    }
+// one out-of-line copy of the segment-box routine with everything passed in registers
+__device__ __noinline__ float segbox_dist2_regs(float a0, float a1, float a2, float d0, float d1, float d2, float h0,
+                                                float h1, float h2) {
+    const float a[3] = {a0, a1, a2}, d[3] = {d0, d1, d2}, h[3] = {h0, h1, h2};
+    return segbox_dist2_local(a, d, h);
 }
 
-// rare path: rounded boxes whose cores are separated by less than r_a + r_b along every SAT axis
-__device__ __noinline__ float box_box_exact_dist(const float* cA, const float* RA, const float* hA, const float* cB,
-                                                 const float* RB, const float* hB) {
+// min squared distance of the 12 edges of box X (centre c, axes x0 x1 x2 given in the frame of box Y, half
+// extents hX) to box Y = [-hY, hY]
+__device__ __forceinline__ float box_edges_vs_box(const float* c, const float (&x)[3][3], const float* hX, const float* hY) {
     float best = 3.0e38f;
-    for (int e = 0; e < 12; e++) {
-        float seg[6], a[3], b[3], d[3];
-        box_edge(cA, RA, hA, e, seg);
-        to_box_local(cB, RB, seg, a);
-        to_box_local(cB, RB, seg + 3, b);
-        d[0] = b[0] - a[0]; d[1] = b[1] - a[1]; d[2] = b[2] - a[2];
-        best = fminf(best, segbox_dist2_local(a, d, hB));
-        box_edge(cB, RB, hB, e, seg);
-        to_box_local(cA, RA, seg, a);
-        to_box_local(cA, RA, seg + 3, b);
-        d[0] = b[0] - a[0]; d[1] = b[1] - a[1]; d[2] = b[2] - a[2];
-        best = fminf(best, segbox_dist2_local(a, d, hA));
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        const int u = (ax + 1) % 3, v = (ax + 2) % 3;
+#pragma unroll 1
+        for (int sgn = 0; sgn < 4; sgn++) {
+            const float su = (sgn & 1) ? hX[u] : -hX[u], sv = (sgn & 2) ? hX[v] : -hX[v];
+            float a[3], d[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float base = fmaf(su, x[u][k], fmaf(sv, x[v][k], c[k]));
+                a[k] = fmaf(-hX[ax], x[ax][k], base);
+                d[k] = 2.f * hX[ax] * x[ax][k];
+            }
+            best = fminf(best, segbox_dist2_regs(a[0], a[1], a[2], d[0], d[1], d[2], hY[0], hY[1], hY[2]));
+        }
     }
-    return sqrtf(best);
+    return best;
+}
+
+// rare path: rounded boxes whose cores are separated by less than r_a + r_b along every SAT axis.
+// The closest features of two disjoint boxes always include an edge (a vertex is the end of one), so the
+// distance is the minimum over the 24 edge-versus-box distances.
+__device__ __forceinline__ float box_box_exact_dist(const float (&R)[3][3], const float (&t)[3], const float* hA,
+                                                    const float* hB) {
+    // B's axes in A's frame are the columns of R; A's axes in B's frame are its rows; cA in B's frame = -R^T t
+    float xb[3][3], tb[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        tb[j] = -dot3(t[0], t[1], t[2], R[0][j], R[1][j], R[2][j]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) xb[j][k] = R[k][j];
+    }
+    const float eb = box_edges_vs_box(t, xb, hB, hA);  // edges of B against A, in A's frame
+    const float ea = box_edges_vs_box(tb, R, hA, hB);  // edges of A against B, in B's frame
+    return sqrtf(fminf(ea, eb));
 }
 
 __device__ __forceinline__ float d_box_box(const float* cA, const float* RA, const float* hA, const float* cB,
                                            const float* RB, const float* hB, float rsum) {
-    float s = box_box_sat(cA, RA, hA, cB, RB, hB);
+    float R[3][3], t[3];
+    box_box_rel(cA, RA, cB, RB, R, t);
+    const float s = box_box_sat(R, t, hA, hB);
     if (s <= 0.f || s >= rsum) return s - rsum;
-    return box_box_exact_dist(cA, RA, hA, cB, RB, hB) - rsum;
+    return box_box_exact_dist(R, t, hA, hB) - rsum;
 }
 
 // ---- upright cylinders (z-prisms) --------------------------------------------------------

@@ -33,6 +33,12 @@ constexpr int TILE = 32;
 constexpr int MAX_WARPS = 4;  // warps cooperating on one tile of 32 configurations: 2 or 4 (template parameter)
 constexpr unsigned FULL = 0xffffffffu;
 
+// The one dynamic shared-memory window of every kernel in this file.  It is declared at file scope so
+// that out-of-line device functions can rebuild their pointers from it (see TileArgs): a pointer
+// passed through a call boundary is generic (LD.E / ATOM.E with 64-bit address arithmetic), a pointer
+// derived from this symbol is known to be shared (LDS / STS / ATOMS, 32-bit addresses).
+extern __shared__ __align__(128) unsigned char smem_raw[];
+
 struct Smem {
     uint32_t* blob;  // staged scene blob
     float* q[2];     // configuration tiles [TILE][D]
@@ -147,13 +153,21 @@ __device__ __forceinline__ void fk_phase(const uint32_t* bi, const float* q, flo
                     sincosf(q[qi + 2], &s, &co);
                     rot_cols(R, 0, 1, co, s);
                 } break;
-                case MRB_J_TRANS_X:
-                case MRB_J_TRANS_Y:
-                case MRB_J_TRANS_Z: {
-                    float x = q[qi];
-                    const int col = code - MRB_J_TRANS_X;
+                // (constant column per case: a run-time column index would push R into local memory)
+                case MRB_J_TRANS_X: {
+                    const float x = q[qi];
 #pragma unroll
-                    for (int r = 0; r < 3; r++) t[r] = fmaf(R[r * 3 + col], x, t[r]);
+                    for (int r = 0; r < 3; r++) t[r] = fmaf(R[r * 3], x, t[r]);
+                } break;
+                case MRB_J_TRANS_Y: {
+                    const float x = q[qi];
+#pragma unroll
+                    for (int r = 0; r < 3; r++) t[r] = fmaf(R[r * 3 + 1], x, t[r]);
+                } break;
+                case MRB_J_TRANS_Z: {
+                    const float x = q[qi];
+#pragma unroll
+                    for (int r = 0; r < 3; r++) t[r] = fmaf(R[r * 3 + 2], x, t[r]);
                 } break;
                 default: break;
             }
@@ -248,6 +262,19 @@ struct TileCtx {
     }
 };
 
+// What crosses an out-of-line call: byte offsets into smem_raw instead of pointers.
+struct TileArgs {
+    uint32_t o_blob, o_W, o_sflag, o_pen, o_queue;
+    bool rule;
+};
+__device__ __forceinline__ TileCtx make_ctx(const TileArgs& a) {
+    const uint32_t* bi = reinterpret_cast<const uint32_t*>(smem_raw + a.o_blob);
+    unsigned* pen = reinterpret_cast<unsigned*>(smem_raw + a.o_pen);
+    return TileCtx{bi, reinterpret_cast<const float*>(bi), reinterpret_cast<const float*>(smem_raw + a.o_W),
+                   smem_raw + a.o_sflag, pen, pen + TILE, reinterpret_cast<uint32_t*>(smem_raw + a.o_queue),
+                   (int)bi[MRB_H_OFF_SHAPES], (int)bi[MRB_H_NMOV], (int)(threadIdx.x & 31), a.rule};
+}
+
 // segments live in W as (midpoint, half vector); static blob rows hold (a, b)
 __device__ __forceinline__ void load_seg(const TileCtx& c, int s, int cfg, float* ab) {
     float v[6];
@@ -332,8 +359,9 @@ __device__ __forceinline__ float narrow_pair(const TileCtx& c, int a, int b, int
 
 // queue entry: bits 0..4 configuration, bits 5..28 record index inside its sublist, bits 29..30 sublist
 template <int T>
-__device__ __noinline__ void drain(const TileCtx c, uint32_t entry, bool valid) {  // by value: keeps the context in registers
+__device__ __noinline__ void drain(const TileArgs args, uint32_t entry, bool valid) {
     if (valid) {
+        const TileCtx c = make_ctx(args);
         const int cfg = entry & 31;
         const int hdr = MRB_H_BP + (T * MRB_BP_SUBLISTS + (int)(entry >> 29)) * 2;
         // a sublist's n records (2 words each) are followed by its n packed pair ids
@@ -343,7 +371,7 @@ __device__ __noinline__ void drain(const TileCtx c, uint32_t entry, bool valid) 
     }
 }
 
-__device__ __noinline__ void drain_any(const TileCtx c, int type, uint32_t entry, bool valid) {
+__device__ __noinline__ void drain_any(const TileArgs c, int type, uint32_t entry, bool valid) {
     switch (type) {  // warp-uniform
         case MRB_PT_SEG_SEG: drain<MRB_PT_SEG_SEG>(c, entry, valid); break;
         case MRB_PT_SEG_BOX: drain<MRB_PT_SEG_BOX>(c, entry, valid); break;
@@ -359,6 +387,7 @@ __device__ __noinline__ void drain_any(const TileCtx c, int type, uint32_t entry
 // per set bit, and drains 32 entries at a time through the exact narrowphase.
 struct Survivors {
     const TileCtx c;  // a copy: a reference would force the context into local memory
+    const TileArgs args;
     int type, qn;
     __device__ __forceinline__ void flush(uint32_t mask, int first_record, int sub) {
         const unsigned lt = (1u << c.lane) - 1u;
@@ -379,14 +408,14 @@ struct Survivors {
                 qn -= TILE;
                 if (c.lane < qn) c.queue[c.lane] = tail;
                 __syncwarp();
-                drain_any(c, type, entry, true);
+                drain_any(args, type, entry, true);
             }
         }
     }
     __device__ __forceinline__ void finish() {
         if (qn > 0) {
             const uint32_t entry = c.queue[c.lane];
-            drain_any(c, type, entry, c.lane < qn);
+            drain_any(args, type, entry, c.lane < qn);
         }
         qn = 0;
         __syncwarp();
@@ -395,14 +424,15 @@ struct Survivors {
 
 // One routine for every queued pair type: the broadphase only needs the records.
 template <int WARPS>
-__device__ __noinline__ void run_queued_types(const TileCtx c, int warp, bool skip_decided, unsigned tol_fx) {
+__device__ __noinline__ void run_queued_types(const TileArgs args, int warp, bool skip_decided, unsigned tol_fx) {
+    const TileCtx c = make_ctx(args);
     const uint32_t* bi = c.bi;
     const float* bf = c.bf;
     const int lane = c.lane;
     const char* Wl = reinterpret_cast<const char*>(c.W + lane);  // this lane's column of W
     const float4* scentre = reinterpret_cast<const float4*>(bf + bi[MRB_H_OFF_SCENTRE]);
     for (int type = 0; type <= MRB_PT_BOX_BOX; ++type) {
-        Survivors sv{c, type, 0};  // one queue per pair type: partial batches only at the end of a type
+        Survivors sv{c, args, type, 0};  // one queue per pair type: partial batches only at the end of a type
         for (int sub = 0; sub < MRB_BP_SUBLISTS; ++sub) {
             const int n = bi[MRB_H_BP + (type * MRB_BP_SUBLISTS + sub) * 2 + 1];
             if (n == 0) continue;
@@ -504,7 +534,10 @@ __device__ __forceinline__ float process_tile(const Smem& sm, const float* q_til
     // a configuration is decided once its accumulated penetration exceeds tol - static part
     const float budget = fmaxf(tol - static_pen, 0.f);
     const unsigned tol_fx = (unsigned)fminf(budget * PEN_SCALE, 4.0e9f);
-    run_queued_types<WARPS>(ctx, warp, early, tol_fx);
+    const TileArgs args{(uint32_t)((const unsigned char*)sm.blob - smem_raw), (uint32_t)((const unsigned char*)sm.W - smem_raw),
+                        (uint32_t)((const unsigned char*)sm.sflag - smem_raw), (uint32_t)((const unsigned char*)sm.pen_fx - smem_raw),
+                        (uint32_t)((const unsigned char*)(sm.queue + warp * QCAP) - smem_raw), rule};
+    run_queued_types<WARPS>(args, warp, early, tol_fx);
     run_type_direct<MRB_PT_CYLZ_CYLZ, WARPS>(ctx, warp);
     run_type_direct<MRB_PT_BOX_CYLZ, WARPS>(ctx, warp);
     __syncthreads();
@@ -545,7 +578,6 @@ __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob
 template <int WARPS>
 __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel(ConfigParams p) {
     constexpr int THREADS = TILE * WARPS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
     stage_scene(sm, p.blob, p.blob_words, p.n_shapes, p.rule, THREADS);
 
@@ -606,7 +638,6 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
 template <int WARPS>
 __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(EdgeParams p) {
     constexpr int THREADS = TILE * WARPS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
     RobotRule none{};
     stage_scene(sm, p.blob, p.blob_words, p.n_shapes, none, THREADS);
