@@ -40,14 +40,36 @@ WORKLOADS = {
     "2d_handover_1M": ("2d_handover", 1_048_576, 100_000),
     "box_stacking_1M": ("box_stacking", 1_048_576, 8_192),
     "mobile_wall_four_8M": ("mobile_wall_four", 8_388_608, 16_384),
+    # BASELINE config 5: one 64M-configuration sweep, SHARDED over the ranks (strong scaling)
+    "mobile_wall_four_64M": ("mobile_wall_four", 67_108_864, 16_384),
 }
+STRONG = {"mobile_wall_four_64M"}  # total work fixed, split across ranks; every other workload is per GPU (weak)
 DEFAULT = "box_rearrangement_4M"
 METRIC = "config collision checks/sec"
 
 
-def uniform_configs(lim, B, seed):
+def uniform_configs(lim, B, seed, chunk=4_194_304):
+    """uniform in the joint limits like the reference's sampler (np.random.uniform, fp64) rounded to fp32;
+    large batches are drawn chunk by chunk from the same stream"""
     rng = np.random.RandomState(seed)
-    return rng.uniform(lim[0], lim[1], (B, lim.shape[1])).astype(np.float32)
+    if B <= chunk:
+        return rng.uniform(lim[0], lim[1], (B, lim.shape[1])).astype(np.float32)
+    out = np.empty((B, lim.shape[1]), np.float32)
+    for i in range(0, B, chunk):
+        n = min(chunk, B - i)
+        out[i:i + n] = rng.uniform(lim[0], lim[1], (n, lim.shape[1]))
+    return out
+
+
+def ncu_traffic(workload, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this workload's kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by scripts/ncu_summary.py output); None if the
+    capture was taken at another batch size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+        return float(t["dram_bytes"]) if t and int(t["configs"]) == int(B) else None
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -212,6 +234,11 @@ def main():
         return float(t.item())
 
     scene_name, B, E = WORKLOADS[args.workload]
+    strong = args.workload in STRONG
+    if strong:  # this rank's shard of the fixed-size sweep (contiguous row block, dist.shard_range)
+        from multirobot_pathplanning_benchmark_b200.dist import shard_range
+        lo, hi = shard_range(B, rank, world)
+        B = hi - lo
     mk, kw = SCENES[scene_name]
     sc = mk()
     cs = S.compile_blob(sc, kw["tol"])
@@ -297,7 +324,7 @@ def main():
         "frac": achieved / fp32_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, from the committed
         # `ncu --set full` capture (profiles/r1_check_configs_v2_broadphase.txt): 203.5 MB + 17.7 MB
-        "traffic": 221.2e6 if args.workload == DEFAULT else None,
+        "traffic": ncu_traffic(args.workload, B),
         "algorithmic_bytes": (4 * D + 1) * B,
         "bound_note": "FK + narrowphase is FP32-FMA bound (SURVEY.md 8d); the HBM view is reported under 'hbm'",
         "peak_source": "measured live by mrb200_fp32_probe (MEASURED_PEAKS.json has no FP32-SIMT figure)",
@@ -391,9 +418,9 @@ def main():
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "configs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "scene": scene_name, "configs_per_gpu": B, "dof": D,
+        "config": {"workload": args.workload, "scene": scene_name, "configs_per_gpu": B, "configs_total": world * B, "dof": D,
                    "collidable_pairs": int(sum(cs.pair_counts)), "tolerance": cs.tol,
                    "inputs": "uniform in joint limits (np.random.uniform), fp32, resident in HBM",
                    "l2": f"input batch {B * D * 4 / 1e6:.0f} MB > 126 MB L2, streamed once per step",
