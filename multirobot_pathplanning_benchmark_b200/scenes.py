@@ -22,8 +22,19 @@ from .scene import Scene, Tf
 S2 = 0.707107
 
 
-def add_ur10(sc: Scene, prefix: str, parent: str, base_rel: Tf, tool: str, q0=None) -> None:
-    """UR10 with collision capsules.  `tool` in {"vacuum", "two_finger", None}."""
+UR10_FILES = {"vacuum": "ur10/ur10_vacuum.g", "two_finger": "ur10/ur10_two_finger.g", None: "ur10/ur10.g"}
+MOBILE_FILE = "mobile-manipulator-restricted.g"
+
+
+def add_ur10(sc: Scene, prefix: str, parent: str, base_rel: Tf, tool: str, q0=None, models_dir=None) -> None:
+    """UR10 with collision capsules.  `tool` in {"vacuum", "two_finger", None}.  With `models_dir` (the
+    reference's P/assets/models/rai directory) the robot is read from the reference's own `.g` file
+    (gfile.add_g_model) instead of the transcription below; tests/test_gfile.py checks both give the same scene."""
+    if models_dir is not None:
+        import os
+        from .gfile import add_g_model
+        add_g_model(sc, os.path.join(models_dir, UR10_FILES[tool]), prefix, parent, base_rel, robot=prefix)
+        return
     p = prefix + "ur_"
     rob = prefix
     lim = {  # ur10.g:34-39
@@ -78,10 +89,16 @@ def add_ur10(sc: Scene, prefix: str, parent: str, base_rel: Tf, tool: str, q0=No
         sc.add(p + "finger2", b, rel=left @ Tf.from_pose([0, -.009, .025]), shape="capsule", size=[.04, .02], contact=-2)
 
 
-def add_mobile_manipulator(sc: Scene, prefix: str, z: float, q0_base) -> None:
+def add_mobile_manipulator(sc: Scene, prefix: str, z: float, q0_base, models_dir=None) -> None:
     """mobile-manipulator-restricted.g:1-68; `world` frame moved to height z
-    (rai_config.py:7708)."""
+    (rai_config.py:7708).  `models_dir`: read the reference's `.g` file instead (see add_ur10)."""
     p, rob = prefix, prefix
+    if models_dir is not None:
+        import os
+        from .gfile import add_g_model
+        add_g_model(sc, os.path.join(models_dir, MOBILE_FILE), prefix, None, Tf(None, [0, 0, z]), robot=rob,
+                    q0={"base": q0_base})
+        return
     sc.add(p + "world", None, rel=[0, 0, z])
     sc.add(p + "base", p + "world", joint="transXYPhi", limits=[[-2, 4], [-2, 2], [-3.14, 3.14]], q0=q0_base, robot=rob)
     sc.add(p + "base_coll", p + "base", shape="ssBox", size=[.4, .4, .4, .05], contact=1)
@@ -128,7 +145,7 @@ _UR_QUAT_NEG = [0.7071, 0, 0, -0.7071]
 _UR_QUAT_POS = [0.7071, 0, 0, 0.7071]
 
 
-def make_box_rearrangement(num_robots: int = 2, num_boxes: int = 9) -> Scene:
+def make_box_rearrangement(num_robots: int = 2, num_boxes: int = 9, models_dir=None) -> Scene:
     """rai.box_rearrangement scene (rai_config.py:2947-3024): UR10 + vacuum tools."""
     sc = Scene()
     sc.add("table", None, rel=[0, 0, .2], shape="box", size=[2, 3, .06], contact=1)
@@ -136,7 +153,7 @@ def make_box_rearrangement(num_robots: int = 2, num_boxes: int = 9) -> Scene:
              ([.5, -.6, 0], _UR_QUAT_POS), ([-.5, -.6, 0], _UR_QUAT_POS)]
     for i in range(num_robots):
         pos, quat = bases[i]
-        add_ur10(sc, f"a{i + 1}_", "table", Tf.from_pose(pos + quat), "vacuum")
+        add_ur10(sc, f"a{i + 1}_", "table", Tf.from_pose(pos + quat), "vacuum", models_dir=models_dir)
     w, d, size = 3, 3, 0.1
     cnt = 0
     for k in range(d):
@@ -149,7 +166,7 @@ def make_box_rearrangement(num_robots: int = 2, num_boxes: int = 9) -> Scene:
     return sc
 
 
-def make_box_stacking(num_robots: int = 4, num_boxes: int = 8) -> Scene:
+def make_box_stacking(num_robots: int = 4, num_boxes: int = 8, models_dir=None) -> Scene:
     """rai.box_stacking scene (rai_config.py:3319-3494): UR10 + Robotiq two-finger tools."""
     sc = Scene()
     sc.add("table", None, rel=[0, 0, .2 - .03], shape="box", size=[3, 3, .06], contact=1)
@@ -157,7 +174,7 @@ def make_box_stacking(num_robots: int = 4, num_boxes: int = 8) -> Scene:
              ([.5, -.6, .03], _UR_QUAT_POS), ([-.5, -.6, .03], _UR_QUAT_POS)]
     for i in range(num_robots):
         pos, quat = bases[i]
-        add_ur10(sc, f"a{i + 1}_", "table", Tf.from_pose(pos + quat), "two_finger")
+        add_ur10(sc, f"a{i + 1}_", "table", Tf.from_pose(pos + quat), "two_finger", models_dir=models_dir)
     w, d, size, height = 3, 3, 0.05, 0.065
     cnt = 0
     for k in range(d):
@@ -170,12 +187,12 @@ def make_box_stacking(num_robots: int = 4, num_boxes: int = 8) -> Scene:
     return sc
 
 
-def make_mobile_wall(num_robots: int = 4) -> Scene:
+def make_mobile_wall(num_robots: int = 4, models_dir=None) -> Scene:
     """rai.dep_mobile_wall_four scene (rai_config.py:7690-7768)."""
     sc = Scene()
     sc.add("table", None, rel=[0, 0, -.02], shape="box", size=[20, 20, .06], contact=1)
     for i in range(num_robots):
-        add_mobile_manipulator(sc, f"a{i}_", 0.25, [2.5, -(num_robots - 1) / 2 + i, -np.pi / 2])
+        add_mobile_manipulator(sc, f"a{i}_", 0.25, [2.5, -(num_robots - 1) / 2 + i, -np.pi / 2], models_dir=models_dir)
     w, h = num_robots, 2
     size = np.array([.5, .25, .15])
     for i in range(h):

@@ -1,0 +1,152 @@
+"""`.g` model reader (gfile.py) and the geometry of the shipped scenes against the reference's own model files.
+
+Two layers: (1) everywhere: scenes.py (the transcription that runs on the GPU box) against
+tests/golden/g_models.json, which scripts/make_golden_gmodels.py derived from the reference's `.g` files;
+(2) in the build container (reference checkout present): the same comparison live, plus identical oracle flags
+for scenes assembled from the files.  Parser unit tests use small synthetic files."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from multirobot_pathplanning_benchmark_b200 import gfile
+from multirobot_pathplanning_benchmark_b200 import scene as S
+from multirobot_pathplanning_benchmark_b200 import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODELS = "/root/reference/src/multi_robot_multi_goal_planning/assets/models/rai"
+MAKERS = {"box_rearrangement": scenes.make_box_rearrangement, "box_stacking": scenes.make_box_stacking,
+          "mobile_wall_four": scenes.make_mobile_wall}
+
+
+@pytest.fixture(scope="module")
+def golden_models():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "g_models.json")))["scenes"]
+
+
+@pytest.mark.parametrize("name", sorted(MAKERS))
+def test_shipped_scene_equals_reference_model_files(golden_models, name):
+    g = golden_models[name]
+    sc = MAKERS[name]()
+    assert sc.dof == g["dof"] and sc.robots == g["robots"]
+    assert np.array_equal(sc.limits(), np.array(g["limits"]))
+    assert np.array_equal(sc.home(), np.array(g["home"]))
+    shapes = sc.collision_shapes()
+    assert set(shapes) == set(g["shapes"])
+    for n in shapes:
+        f, e = sc.frames[n], g["shapes"][n]
+        assert f.shape.kind == e["kind"] and list(map(float, f.shape.size)) == e["size"] and f.contact == e["contact"], n
+    assert sorted(sorted(p) for p in sc.collidable_pairs()) == g["pairs"]
+    for q, poses in zip(g["configs"], g["poses"]):
+        X = sc.fk(np.array(q))
+        for n in shapes:
+            got = np.concatenate([X[n].t, X[n].R.ravel()])
+            assert np.abs(got - np.array(poses[n])).max() < 1e-11, n
+
+
+@pytest.mark.skipif(not os.path.isdir(MODELS), reason="reference checkout not available")
+@pytest.mark.parametrize("name", sorted(MAKERS))
+def test_scene_from_g_files_gives_identical_oracle_flags(name):
+    from oracle import oracle_scene as O
+    tol = scenes.SCENES[name][1]["tol"]
+    a, b = MAKERS[name](), MAKERS[name](models_dir=MODELS)
+    ca, cb = S.compile_blob(a, tol), S.compile_blob(b, tol)
+    assert ca.pairs == cb.pairs and ca.shape_names == cb.shape_names
+    lim = a.limits()
+    q = np.random.RandomState(3).uniform(lim[0], lim[1], (3000, a.dof))
+    fa, pa, _ = O.check_configs(ca.blob64, q)
+    fb, pb, _ = O.check_configs(cb.blob64, q)
+    assert np.array_equal(fa, fb)
+    assert np.abs(pa - pb).max() < 1e-12
+
+
+@pytest.mark.skipif(not os.path.isdir(MODELS), reason="reference checkout not available")
+def test_golden_file_is_current(golden_models):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import make_golden_gmodels as G
+    for name, mk in MAKERS.items():
+        fresh = json.loads(json.dumps(G.summary(mk(models_dir=MODELS))))
+        assert fresh == golden_models[name], name
+
+
+# ---- parser unit tests on synthetic files --------------------------------------------------------------------
+def write(tmp_path, name, text):
+    p = tmp_path / name
+    p.write_text(text)
+    return str(p)
+
+
+def test_parser_include_prefix_edit(tmp_path):
+    write(tmp_path, "inner.g", """
+link0: { multibody: true }
+j1_origin(link0): { rel: [0, 0, 0.5, 1, 0, 0, 0] }
+j1(j1_origin): { joint: hingeZ, limits: [-1, 2, 9, 9, 9] }   # trailing velocity / effort entries are ignored
+tip(j1) { Q:"t(0 0 .25) d(90 1 0 0)" shape:capsule size:[.2 .05], contact:-1 }
+vis(j1): { shape: mesh, mesh: <meshes/x.ply>, visual: True }
+""")
+    top = write(tmp_path, "top.g", """
+base: {}
+Prefix: "r_"
+Include: <inner.g>
+Prefix: false
+Edit r_link0(base): {}
+Edit r_j1: { q: 0.5 }
+ball (r_tip){ shape:sphere, size:[.03]   # no comma, comment after value
+  Q: [0.1, 0, 0]
+  contact: 1 }
+ball (ball){ shape:marker, size:[.3] contact:0 }
+Edit ball(r_tip) { Q:"t(.2 0 0)" }
+""")
+    fr = {f.name: f for f in gfile.load_g(top) if not (f.name == "ball" and f.parent == "ball")}
+    assert fr["r_link0"].parent == "base" and fr["r_j1"].attrs["q"] == 0.5
+    assert fr["r_tip"].attrs["size"] == [0.2, 0.05] and fr["r_tip"].attrs["contact"] == -1
+    assert fr["ball"].attrs["Q"] == "t(.2 0 0)"
+    sc = S.Scene()
+    sc.add("world", None)
+    gfile.add_g_model(sc, top, "a_", "world", S.Tf.from_pose([1, 0, 0]), robot="a_")
+    assert sc.dof == 1 and np.array_equal(sc.limits(), [[-1.0], [2.0]]) and sc.home()[0] == 0.5
+    assert sc.collision_shapes() == ["a_r_tip", "a_ball"]
+    assert sc.frames["a_base"].joint == "rigid" and sc.frames["a_base"].parent == "world"
+    X = sc.fk(np.array([np.pi / 2]))
+    # tip: base at x=1, z=.5 up, rotated 90 deg about z, then .25 up
+    assert np.allclose(X["a_r_tip"].t, [1, 0, 0.75])
+    # ball: .2 along the tip's x axis, which points along world y after the joint rotation
+    assert np.allclose(X["a_ball"].t, [1, 0.2, 0.75])
+    # tip and ball share a link (no joint between them): never collide
+    assert sc.collidable_pairs() == []
+
+
+def test_parser_rejects_garbage_and_unknown_joint(tmp_path):
+    bad = write(tmp_path, "bad.g", "a: { joint: ballAndSocket }")
+    with pytest.raises(ValueError):
+        gfile.add_g_model(S.Scene(), bad, "", None, None, robot="r")
+    with pytest.raises(KeyError):
+        gfile.load_g(write(tmp_path, "edit.g", "Edit nothing: { q: 1 }"))
+
+
+# ---- the reference's URDF export of the 2d_handover scene (P/assets/models/pinocchio/2d_handover.urdf) ----------
+URDF_2D = "/root/reference/src/multi_robot_multi_goal_planning/assets/models/pinocchio/2d_handover.urdf"
+
+
+@pytest.mark.skipif(not os.path.isfile(URDF_2D), reason="reference checkout not available")
+def test_two_dim_handover_matches_the_reference_urdf_export():
+    from multirobot_pathplanning_benchmark_b200 import urdf
+    u = urdf.load_urdf(URDF_2D, robot_of=lambda j: "a1" if "_a1_" in j else "a2")
+    s = scenes.make_two_dim_handover()
+    assert u.dof == s.dof == 6
+    assert np.allclose(u.limits(), s.limits())
+    Xu, Xs = u.fk(np.zeros(6)), s.fk(np.zeros(6))
+    ref_u, ref_s = Xu["table"].inv(), Xs["table"].inv()
+    for n in s.collision_shapes():
+        fu, fs = u.frames[n], s.frames[n]
+        assert fu.shape.kind == fs.shape.kind and np.allclose(fu.shape.size[:3], fs.shape.size[:3]), n
+        a, b = ref_u @ Xu[n], ref_s @ Xs[n]
+        assert np.allclose(a.t, b.t, atol=1e-12) and np.allclose(a.R, b.R, atol=1e-12), n
+    # moving an agent moves it identically in both models (x, y, phi about z)
+    q = np.array([0.3, -0.7, 1.1, -1.2, 0.4, -2.0])
+    Xu, Xs = u.fk(q), s.fk(q)
+    for n in ("a1", "a2"):
+        a, b = Xu["table"].inv() @ Xu[n], Xs["table"].inv() @ Xs[n]
+        assert np.allclose(a.t, b.t, atol=1e-12) and np.allclose(a.R, b.R, atol=1e-12)
