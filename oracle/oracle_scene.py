@@ -19,7 +19,8 @@ _LIB = None
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle_scene.so")
     src = os.path.join(_HERE, "oracle_scene.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    hdr = os.path.join(_HERE, "..", "multirobot_pathplanning_benchmark_b200", "csrc", "scene_blob.h")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
 
