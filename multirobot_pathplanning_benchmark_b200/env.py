@@ -80,6 +80,72 @@ class CudaDevice:
 
 
 # ----------------------------------------------------------------------------------------------
+# speculative batching behind the single-query API
+# ----------------------------------------------------------------------------------------------
+class SpeculativeCache:
+    """Turns the planners' one-query-at-a-time calls into whole-batch device launches without touching
+    planner code, and without changing a single answer:
+
+      * uniform samples: the reference draws them in blocks of 1000 (`_make_uniform_sampler`,
+        P/problems/planning_env.py:1697-1708) and the rejection samplers then ask `is_collision_free` row
+        by row (P/planners/collision_free_sampler.py:106-112).  The first such query validates the whole
+        block in the query's mode with one launch; the other 999 answers come from the cached flags.
+      * edges: planners revisit an edge with growing windows `N_start / N_max` over the reference's binary
+        order (P/problems/rai_base_env.py:618-676; IT* sparse-then-dense checks, the interleaved path check
+        P/problems/planning_env.py:1827-1874).  The first query scans the whole edge once and stores the first
+        colliding position p0; a window [a, b) is free iff p0 is none or p0 >= b, collides iff a <= p0 < b,
+        and only a window that starts after a known collision goes back to the device.
+
+    Keys are the exact fp64 bytes of the configurations, so a configuration that was edited after sampling
+    (pinned robots) simply misses the cache and takes the normal path."""
+
+    def __init__(self, max_edges: int = 1 << 18):
+        self.block: Optional[np.ndarray] = None
+        self.block_index: Dict[bytes, int] = {}
+        self.block_flags: Dict[int, np.ndarray] = {}
+        self.edges: Dict[tuple, int] = {}
+        self.max_edges = max_edges
+        self.stats = {"config_launches": 0, "config_hits": 0, "edge_launches": 0, "edge_hits": 0}
+
+    def new_block(self, batch: np.ndarray) -> None:
+        self.block = batch
+        self.block_index = {batch[i].tobytes(): i for i in range(len(batch))}
+        self.block_flags = {}
+
+    def config_flag(self, slot: int, q_state: np.ndarray, check_batch) -> Optional[bool]:
+        """flag of a configuration of the current sample block in mode slot `slot`, or None if it is not one"""
+        i = self.block_index.get(np.ascontiguousarray(q_state, np.float64).tobytes())
+        if i is None:
+            return None
+        flags = self.block_flags.get(slot)
+        if flags is None:
+            flags = np.asarray(check_batch(self.block)).astype(bool)
+            self.block_flags[slot] = flags
+            self.stats["config_launches"] += 1
+        else:
+            self.stats["config_hits"] += 1
+        return bool(flags[i])
+
+    def edge_window(self, key: tuple, n_start: int, n_max: Optional[int], N: int, full_scan) -> Optional[bool]:
+        """answer for window [n_start, n_max) of the edge `key`, or None if only the device can tell"""
+        first = self.edges.get(key)
+        if first is None:
+            first = int(full_scan())
+            if len(self.edges) >= self.max_edges:
+                self.edges.clear()
+            self.edges[key] = first
+            self.stats["edge_launches"] += 1
+        else:
+            self.stats["edge_hits"] += 1
+        hi = N if n_max is None else min(n_max, N)
+        if first < 0 or first >= hi:
+            return True
+        if first >= n_start:
+            return False
+        return None
+
+
+# ----------------------------------------------------------------------------------------------
 # geometry + modes, independent of the reference package
 # ----------------------------------------------------------------------------------------------
 class SceneModel:
@@ -148,8 +214,9 @@ if HAVE_REFERENCE:
         raises ValueError on q=None like abstract_env.py:256-257; a failing device call raises
         (never reports "free")."""
 
-        def __init__(self, scene: Scene, tol: float, resolution: float, device=None):
+        def __init__(self, scene: Scene, tol: float, resolution: float, device=None, speculate: bool = True):
             self.model = SceneModel(scene, tol, resolution, device=device)
+            self.spec_cache = SpeculativeCache() if speculate else None
             self.scene = scene
             self.robots = list(scene.robots)
             sl = scene.robot_slices()
@@ -239,11 +306,28 @@ if HAVE_REFERENCE:
             mode._cached_hash = None
             return sg
 
+        # ---- sampling: the reference's block sampler, with the block handed to the speculation cache ----
+        def _make_uniform_sampler(self, batch_size=1000):
+            """Same random stream and same yielded configurations as BaseProblem._make_uniform_sampler
+            (planning_env.py:1697-1708)."""
+            while True:
+                batch = np.random.uniform(low=self.limits[0, :], high=self.limits[1, :], size=(batch_size, self.limits.shape[1]))
+                if self.spec_cache is not None:
+                    self.spec_cache.new_block(batch)
+                for i in range(batch_size):
+                    yield self.start_pos.from_flat(batch[i])
+
         # ---- collision queries -------------------------------------------------------------
         def is_collision_free(self, q, m, collision_tolerance: Optional[float] = None) -> bool:
             if q is None:
                 raise ValueError
             self.set_to_mode(m)
+            if self.spec_cache is not None and collision_tolerance is None:
+                slot = self._slot
+                hit = self.spec_cache.config_flag(slot, q.state(), lambda b: CudaDevice.to_numpy(
+                    self.model.device.check_configs(slot, b.astype(np.float32))))
+                if hit is not None:
+                    return hit
             out = self.model.device.check_configs(self._slot, np.asarray(q.state(), np.float32)[None], collision_tolerance)
             return bool(CudaDevice.to_numpy(out)[0])
 
@@ -287,9 +371,19 @@ if HAVE_REFERENCE:
             if N_start > N:
                 assert False
             self.set_to_mode(m)
-            free, _ = self.model.device.check_edges(
-                self._slot, np.asarray(q1.state(), np.float32)[None], np.asarray(q2.state(), np.float32)[None], resolution,
-                N=np.array([N], np.int32), n_start=N_start, n_max=N_max, include_endpoints=include_endpoints, tol=tolerance)
+            a, b = np.asarray(q1.state(), np.float32)[None], np.asarray(q2.state(), np.float32)[None]
+            Ns = np.array([N], np.int32)
+            if self.spec_cache is not None:
+                slot = self._slot
+                key = (slot, q1.state().tobytes(), q2.state().tobytes(), int(N), float(resolution), bool(include_endpoints),
+                       None if tolerance is None else float(tolerance))
+                hit = self.spec_cache.edge_window(key, N_start, N_max, int(N), lambda: CudaDevice.to_numpy(
+                    self.model.device.check_edges(slot, a, b, resolution, N=Ns, include_endpoints=include_endpoints,
+                                                  tol=tolerance)[1])[0])
+                if hit is not None:
+                    return hit
+            free, _ = self.model.device.check_edges(self._slot, a, b, resolution, N=Ns, n_start=N_start, n_max=N_max,
+                                                    include_endpoints=include_endpoints, tol=tolerance)
             return bool(CudaDevice.to_numpy(free)[0])
 
         def is_path_collision_free(self, path, binary_order: bool = True, resolution=None, tolerance=None,
@@ -376,9 +470,9 @@ if HAVE_REFERENCE:
     class b200_two_dim_handover(SequenceMixin, B200Env):
         """B200 counterpart of rai.2d_handover (rai_envs.py:462-573)."""
 
-        def __init__(self, device=None):
+        def __init__(self, device=None, speculate: bool = True):
             mk, kw = SCENES["2d_handover"]
-            B200Env.__init__(self, mk(), kw["tol"], kw["resolution"], device=device)
+            B200Env.__init__(self, mk(), kw["tol"], kw["resolution"], device=device, speculate=speculate)
             self.manipulating_env = True
             self.tasks = _two_dim_handover_tasks(self)
             self.sequence = self._make_sequence_from_names(
@@ -391,9 +485,9 @@ if HAVE_REFERENCE:
         goal, then all return home.  (The reference's pick / place keyframes come from rai's KOMO.)"""
 
         class _Env(SequenceMixin, B200Env):
-            def __init__(self, device=None):
+            def __init__(self, device=None, speculate: bool = True):
                 mk, kw = SCENES[scene_name]
-                B200Env.__init__(self, mk(), kw["tol"], kw["resolution"], device=device)
+                B200Env.__init__(self, mk(), kw["tol"], kw["resolution"], device=device, speculate=speculate)
                 rng = np.random.RandomState(seed)
                 lim = self.limits
                 slot = self.model.slot_for(())
@@ -447,9 +541,19 @@ if HAVE_REFERENCE:
         """abstract.test (abstract_env.py:381-421) with every collision query answered by the fp64 CUDA
         kernels; flags are bit-identical, so planners behave exactly as on the reference's own env."""
 
-        def __init__(self, device=None):
+        def __init__(self, device=None, speculate: bool = True):
+            self.spec_cache = SpeculativeCache() if speculate else None
             super().__init__()
             self._device = device
+
+        def _make_uniform_sampler(self, batch_size=1000):
+            """planning_env.py:1697-1708, plus the block hand-off to the speculation cache"""
+            while True:
+                batch = np.random.uniform(low=self.limits[0, :], high=self.limits[1, :], size=(batch_size, self.limits.shape[1]))
+                if self.spec_cache is not None:
+                    self.spec_cache.new_block(batch)
+                for i in range(batch_size):
+                    yield self.start_pos.from_flat(batch[i])
 
         @property
         def device(self):
@@ -463,6 +567,10 @@ if HAVE_REFERENCE:
         def is_collision_free(self, q, mode):
             if q is None:
                 raise ValueError
+            if self.spec_cache is not None:
+                hit = self.spec_cache.config_flag(0, q.state(), lambda b: self.device.check_configs(b))
+                if hit is not None:
+                    return hit
             return bool(self.device.check_configs(q.state()[None])[0])
 
         def is_edge_collision_free(self, q1, q2, mode, resolution=None, tolerance=None, include_endpoints=False, N_start=0,
@@ -473,7 +581,14 @@ if HAVE_REFERENCE:
                 N = max(2, int(config_dist(q1, q2, "max") / resolution) + 1)
             if N_start > N:
                 assert False
-            f, _ = self.device.check_edges(q1.state()[None], q2.state()[None], resolution, N=np.array([N], np.int32),
+            Ns = np.array([N], np.int32)
+            if self.spec_cache is not None:  # (the abstract env ignores `tolerance`, abstract_env.py:301-354)
+                key = (0, q1.state().tobytes(), q2.state().tobytes(), int(N), float(resolution), bool(include_endpoints))
+                hit = self.spec_cache.edge_window(key, N_start, N_max, int(N), lambda: self.device.check_edges(
+                    q1.state()[None], q2.state()[None], resolution, N=Ns, include_endpoints=include_endpoints)[1][0])
+                if hit is not None:
+                    return hit
+            f, _ = self.device.check_edges(q1.state()[None], q2.state()[None], resolution, N=Ns,
                                            n_start=N_start, n_max=N_max, include_endpoints=include_endpoints)
             return bool(f[0])
 

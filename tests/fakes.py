@@ -38,9 +38,12 @@ class OracleSceneDevice:
 class OracleAbstractDevice:
     def __init__(self):
         self.sc = OA.AbstractScene.abstract_test()
+        self.calls = {"configs": 0, "edges": 0}
 
     def check_configs(self, q):
+        self.calls["configs"] += 1
         return self.sc.batch_flags(np.asarray(q, np.float64))
 
     def check_edges(self, q1, q2, resolution, N=None, n_start=0, n_max=None, include_endpoints=False):
+        self.calls["edges"] += 1
         return self.sc.batch_edge_flags(q1, q2, resolution, include_endpoints=include_endpoints, N_start=n_start, N_max=n_max, Ns=N)

@@ -135,3 +135,75 @@ def test_batched_path_check_equals_reference_path_check(reference, envmod):
     assert 0 < agree < 30
     qs = env.sample_valid_uniform_batch(env.start_mode, 100, np.random.RandomState(1))
     assert qs.shape == (100, 6) and all(env.is_collision_free(env.start_pos.from_flat(q), env.start_mode) for q in qs[:10])
+
+
+# ---- speculative batching behind the single-query API ---------------------------------
+@pytest.mark.parametrize("planner", ["prm", "rrt"])
+def test_speculation_changes_no_answer_and_saves_device_calls(reference, envmod, planner):
+    """Same seed with and without the speculation cache: identical plans, far fewer device round trips."""
+    runs = {}
+    for spec in (False, True):
+        dev = OracleAbstractDevice()
+        env = envmod.b200_abstract_test(device=dev, speculate=spec)
+        path, _ = run_planner(env, planner, 5)
+        runs[spec] = (path, dict(dev.calls), None if env.spec_cache is None else dict(env.spec_cache.stats))
+    p0, p1 = runs[False][0], runs[True][0]
+    assert p0 is not None and p1 is not None and len(p0) == len(p1)
+    for a, b in zip(p0, p1):
+        assert np.array_equal(a.q.state(), b.q.state()) and a.mode.task_ids == b.mode.task_ids
+    calls0, calls1, stats = runs[False][1], runs[True][1], runs[True][2]
+    assert sum(calls1.values()) < sum(calls0.values())
+    assert stats["config_hits"] + stats["edge_hits"] > 0
+    print(planner, "device calls without / with speculation:", calls0, calls1, stats)
+    assert calls1["edges"] < calls0["edges"] and calls1["configs"] < calls0["configs"]
+
+
+def test_speculative_edge_windows_equal_direct_queries(envmod):
+    """every (N_start, N_max) window of an edge: cache-served answer == direct device answer"""
+    spec_env = envmod.b200_two_dim_handover(device=OracleSceneDevice(), speculate=True)
+    ref_env = envmod.b200_two_dim_handover(device=OracleSceneDevice(), speculate=False)
+    m = spec_env.start_mode
+    rng = np.random.RandomState(4)
+    lim = spec_env.limits
+    n_coll = 0
+    for _ in range(25):
+        a = rng.uniform(lim[0], lim[1])
+        b = a + rng.uniform(-0.6, 0.6, a.shape)
+        q1, q2 = spec_env.start_pos.from_flat(a), spec_env.start_pos.from_flat(b)
+        whole = ref_env.is_edge_collision_free(q1, q2, ref_env.start_mode)
+        n_coll += not whole
+        N = max(2, int(np.max(np.abs(a - b)) / spec_env.collision_resolution) + 1)
+        for (ns, nm) in ((0, 1), (0, 4), (4, 16), (16, None), (0, None), (3, 5), (N // 2, None), (N, None), (0, 10_000)):
+            if ns > N:  # the reference asserts on N_start > N (rai_base_env.py:640-641)
+                continue
+            got = spec_env.is_edge_collision_free(q1, q2, m, N_start=ns, N_max=nm)
+            want = ref_env.is_edge_collision_free(q1, q2, ref_env.start_mode, N_start=ns, N_max=nm)
+            assert got == want, (ns, nm)
+        for inc in (True, False):
+            assert spec_env.is_edge_collision_free(q1, q2, m, include_endpoints=inc) == \
+                ref_env.is_edge_collision_free(q1, q2, ref_env.start_mode, include_endpoints=inc)
+    assert 3 < n_coll < 25
+    st = spec_env.spec_cache.stats
+    assert st["edge_hits"] > 4 * st["edge_launches"]
+    # (windows that start after a known collision are not decided by p0 and go back to the device)
+    assert spec_env.model.device.calls["edges"] * 1.5 < ref_env.model.device.calls["edges"]
+
+
+def test_speculative_sample_block_serves_rejection_sampling(envmod):
+    dev = OracleSceneDevice()
+    env = envmod.b200_two_dim_handover(device=dev, speculate=True)
+    plain = envmod.b200_two_dim_handover(device=OracleSceneDevice(), speculate=False)
+    np.random.seed(11)
+    qs = [env.sample_config_uniform_in_limits() for _ in range(300)]
+    np.random.seed(11)
+    qs_plain = [plain.sample_config_uniform_in_limits() for _ in range(300)]
+    assert all(np.array_equal(a.state(), b.state()) for a, b in zip(qs, qs_plain))  # same random stream
+    got = [env.is_collision_free(q, env.start_mode) for q in qs]
+    want = [plain.is_collision_free(q, plain.start_mode) for q in qs_plain]
+    assert got == want and 0 < sum(got) < 300
+    assert dev.calls["configs"] == 1 and env.spec_cache.stats["config_hits"] == 299
+    # an edited sample (pinned robot) misses the cache and is answered directly
+    q = qs[0]
+    q[0] = q[0] + 0.01
+    assert env.is_collision_free(q, env.start_mode) == plain.is_collision_free(q, plain.start_mode)
+    assert dev.calls["configs"] == 2
