@@ -41,7 +41,7 @@ struct EdgeParams {
     int* counter;         // device scratch: dynamic edge scheduler
 };
 
-size_t scene_smem_bytes(int blob_words, int D, int world_words, int n_shapes);
+size_t scene_smem_bytes(int blob_words, int D, int world_words, int n_shapes, bool edges = true);
 cudaError_t launch_static_penetration(uint32_t* blob, cudaStream_t st);
 cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st);
 cudaError_t launch_check_edges(const EdgeParams& p, cudaStream_t st);

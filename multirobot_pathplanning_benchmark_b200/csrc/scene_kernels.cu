@@ -48,13 +48,16 @@ struct Smem {
     uint32_t* queue;   // [WARPS][QCAP] surviving (configuration, pair) items
     uint8_t* sflag;  // [n_shapes] bit0 = relevant, bit1 = other robot (A6 rule)
     uint64_t* bar;   // [3] mbarriers: blob, q0, q1
-    int* misc;       // [40] small broadcast scratch (edge kernel)
-    double* ed;      // [2*D] edge start and step (fp64)
+    int* misc;       // [EDGE_MISC] edge kernel bookkeeping (active edge slots, lane assignment)
+    double* ed;      // [EDGE_SLOTS][2*D] start and step of the active edges (fp64)
 };
+
+constexpr int EDGE_SLOTS = 8;    // edges a CTA keeps in flight (refill maps 4 lanes to a slot: 8 x 4 = one warp): short edges share one tile of 32 interpolation points
+constexpr int EDGE_MISC = 8 * EDGE_SLOTS + 2 * 32 + 8;
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-__host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_words, int n_shapes, size_t* off) {
+__host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_words, int n_shapes, bool edges, size_t* off) {
     size_t o = 0;
     off[0] = o; o = align16(o + size_t(blob_words) * 4);
     off[1] = o; o = align16(o + size_t(TILE) * D * 4);
@@ -64,14 +67,14 @@ __host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_w
     off[5] = o; o = align16(o + size_t(MAX_WARPS) * 64 * 4);
     off[6] = o; o = align16(o + size_t(n_shapes));
     off[7] = o; o = align16(o + 3 * 8);
-    off[8] = o; o = align16(o + 40 * 4);
-    off[9] = o; o = align16(o + size_t(2) * D * 8);
+    off[8] = o; o = align16(o + (edges ? EDGE_MISC * 4 : 0));  // the configuration kernel carries no edge state
+    off[9] = o; o = align16(o + (edges ? size_t(EDGE_SLOTS) * 2 * D * 8 : 0));
     return o;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int blob_words, int D, int world_words, int n_shapes) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int blob_words, int D, int world_words, int n_shapes, bool edges) {
     size_t off[10];
-    smem_layout(blob_words, D, world_words, n_shapes, off);
+    smem_layout(blob_words, D, world_words, n_shapes, edges, off);
     Smem s;
     s.blob = (uint32_t*)(base + off[0]);
     s.q[0] = (float*)(base + off[1]);
@@ -87,9 +90,9 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int blob_words, int D
     return s;
 }
 
-size_t scene_smem_bytes(int blob_words, int D, int world_words, int n_shapes) {
+size_t scene_smem_bytes(int blob_words, int D, int world_words, int n_shapes, bool edges) {
     size_t off[10];
-    return smem_layout(blob_words, D, world_words, n_shapes, off);
+    return smem_layout(blob_words, D, world_words, n_shapes, edges, off);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -578,7 +581,7 @@ __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob
 template <int WARPS>
 __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel(ConfigParams p) {
     constexpr int THREADS = TILE * WARPS;
-    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
+    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, false);
     stage_scene(sm, p.blob, p.blob_words, p.n_shapes, p.rule, THREADS);
 
     const int D = p.D;
@@ -632,78 +635,145 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
 }
 
 // ------------------------------------------------------------------------------------------
-// edge batch kernel (A8 batch variant): one CTA per edge at a time, 32 interpolation points
-// per step in the reference's binary order, early exit on the first colliding step
+// edge batch kernel (A8 batch variant).  A CTA keeps up to EDGE_SLOTS edges in flight and fills every tile
+// of 32 interpolation points from them in slot order, so short edges (and short N_start / N_max windows)
+// share a tile instead of leaving most lanes idle; a long edge fills whole tiles on its own.  Positions
+// follow the reference's binary order; an edge retires at its first colliding position (early exit) or
+// when its window is exhausted, and its slot is refilled from the dynamic edge counter.
 // ------------------------------------------------------------------------------------------
 template <int WARPS>
 __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(EdgeParams p) {
     constexpr int THREADS = TILE * WARPS;
-    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes);
+    constexpr int K = EDGE_SLOTS;
+    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, true);
     RobotRule none{};
     stage_scene(sm, p.blob, p.blob_words, p.n_shapes, none, THREADS);
 
     const int D = p.D;
     const float tol = p.tol < 0.f ? reinterpret_cast<const float*>(sm.blob)[MRB_H_TOL] : p.tol;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* s_edge = sm.misc;       // [0] edge id, [1] N, [2] first colliding position
-    int* s_idx = sm.misc + 8;    // [32] interpolation index per lane
-    double* e_start = sm.ed;     // q1 (fp64)
-    double* e_step = sm.ed + D;  // (q2 - q1) / (N - 1)
+    // per slot: edge id (-1 = empty), N, end of the window, next position, lanes taken in this tile, first lane
+    int* s_edge = sm.misc;
+    int* s_N = sm.misc + K;
+    int* s_nmax = sm.misc + 2 * K;
+    int* s_cur = sm.misc + 3 * K;
+    int* s_take = sm.misc + 4 * K;
+    int* s_pref = sm.misc + 5 * K;
+    int* s_idx = sm.misc + 8 * K;        // [32] interpolation index of the lane's sample (-1: idle lane)
+    int* s_slot = s_idx + 32;            // [32] slot the lane's sample belongs to
+    int* s_ctl = s_slot + 32;            // [0] samples in this tile, [1] edge counter exhausted
+    double* e_start = sm.ed;             // [K][D] q1 (fp64)
+    double* e_step = sm.ed + K * D;      // [K][D] (q2 - q1) / (N - 1)
+
+    if (threadIdx.x < K) s_edge[threadIdx.x] = -1;
+    if (threadIdx.x == 0) s_ctl[1] = 0;
+    __syncthreads();
 
     for (;;) {
-        if (threadIdx.x == 0) s_edge[0] = atomicAdd(p.counter, 1);
-        __syncthreads();
-        const int64_t e = s_edge[0];
-        if (e >= p.E) break;
-        // endpoints in fp64, N exactly as the reference: max(2, int(|dq|_inf / resolution) + 1)
         if (warp == 0) {
-            double m = 0.0;
-            for (int k = lane; k < D; k += 32) {
-                const double a = (double)p.q1[e * D + k], b = (double)p.q2[e * D + k];
-                e_start[k] = a;
-                e_step[k] = __dsub_rn(b, a);
-                m = fmax(m, fabs(__dsub_rn(a, b)));
+            // ---- refill empty slots: four lanes set up one slot (32 lanes = EDGE_SLOTS x 4) ----
+            for (;;) {
+                const unsigned nm = __ballot_sync(FULL, lane < K && s_edge[lane] < 0);
+                if (!nm || s_ctl[1]) break;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(p.counter, __popc(nm));
+                base = __shfl_sync(FULL, base, 0);
+                const int g = lane >> 2, j = lane & 3;
+                const int64_t e = (int64_t)base + __popc(nm & ((1u << g) - 1u));
+                const bool mine = ((nm >> g) & 1u) && e < p.E;
+                // endpoints in fp64, N exactly as the reference: max(2, int(|dq|_inf / resolution) + 1)
+                double m = 0.0;
+                if (mine) {
+                    for (int k = j; k < D; k += 4) {
+                        const double a = (double)p.q1[e * D + k], b = (double)p.q2[e * D + k];
+                        e_start[g * D + k] = a;
+                        e_step[g * D + k] = __dsub_rn(b, a);
+                        m = fmax(m, fabs(__dsub_rn(a, b)));
+                    }
+                }
+                m = fmax(m, __shfl_xor_sync(FULL, m, 1));
+                m = fmax(m, __shfl_xor_sync(FULL, m, 2));
+                if (mine) {
+                    const int N = p.N ? p.N[e] : max(2, (int)__ddiv_rn(m, p.resolution) + 1);
+                    const double inv = (double)(N - 1);
+                    for (int k = j; k < D; k += 4) e_step[g * D + k] = __ddiv_rn(e_step[g * D + k], inv);
+                    const int nmax = (p.n_max < 0 || p.n_max > N) ? N : p.n_max;
+                    if (j == 0) {
+                        if (p.n_start < nmax) {
+                            s_edge[g] = (int)e;
+                            s_N[g] = N;
+                            s_nmax[g] = nmax;
+                            s_cur[g] = p.n_start;
+                        } else {  // empty window: free, nothing to check
+                            p.flags[e] = 1;
+                            if (p.first_pos) p.first_pos[e] = -1;
+                        }
+                    }
+                }
+                if (lane == 0 && (int64_t)base + __popc(nm) >= p.E) s_ctl[1] = 1;
+                __syncwarp();
             }
+            // ---- hand the tile's 32 lanes out in slot order ----
+            const int rem = (lane < K && s_edge[lane] >= 0) ? s_nmax[lane] - s_cur[lane] : 0;
+            int incl = rem;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
-            int N = p.N ? p.N[e] : max(2, (int)__ddiv_rn(m, p.resolution) + 1);
-            if (lane == 0) { s_edge[1] = N; s_edge[2] = -1; }
-            const double inv = (double)(N - 1);
-            for (int k = lane; k < D; k += 32) e_step[k] = __ddiv_rn(e_step[k], inv);
+            for (int o = 1; o < K; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int pref = min(incl - rem, TILE);
+            const int take = min(rem, TILE - pref);
+            if (lane < K) { s_pref[lane] = pref; s_take[lane] = take; }
+            const int total = min(__shfl_sync(FULL, incl, K - 1), TILE);
+            __syncwarp();
+            int slot = 0, i = -1;
+            if (lane < total) {
+#pragma unroll
+                for (int k = 1; k < K; k++) slot = (lane >= s_pref[k] && s_take[k] > 0) ? k : slot;
+                const int pos = s_cur[slot] + (lane - s_pref[slot]);
+                const int N = s_N[slot];
+                i = binary_order_index(N, pos);
+                if (!p.include_endpoints && (i == 0 || i == N - 1)) i = -1;
+            }
+            // idle lanes recompute the start point of the last sample's edge (a valid configuration; result unused)
+            const int last_slot = __shfl_sync(FULL, slot, total > 0 ? total - 1 : 0);
+            s_idx[lane] = i;
+            s_slot[lane] = lane < total ? slot : last_slot;
+            if (lane == 0) s_ctl[0] = total;
         }
         __syncthreads();
-        const int N = s_edge[1];
-        const int nmax = (p.n_max < 0 || p.n_max > N) ? N : p.n_max;
-        for (int base = p.n_start; base < nmax; base += TILE) {
-            if (warp == 0) {
-                const int pos = base + lane;
-                int i = -1;
-                if (pos < nmax) {
-                    i = binary_order_index(N, pos);
-                    if (!p.include_endpoints && (i == 0 || i == N - 1)) i = -1;
-                }
-                s_idx[lane] = i;
-            }
-            __syncthreads();
-            // q = q1 + step * i in fp64 (reference order of operations), rounded once to fp32
-            for (int t = threadIdx.x; t < TILE * D; t += THREADS) {
-                const int c = t / D, k = t - c * D;
-                const int i = s_idx[c];
-                sm.q[0][t] = (float)__dadd_rn(e_start[k], __dmul_rn(e_step[k], (double)(i < 0 ? 0 : i)));
-            }
-            __syncthreads();
-            bool relpen;
-            const float total = process_tile<WARPS>(sm, sm.q[0], D, tol, false, false, &relpen);
-            if (warp == 0) {
-                const unsigned hit = __ballot_sync(FULL, s_idx[lane] >= 0 && total > tol);
-                if (lane == 0 && hit) s_edge[2] = base + __ffs(hit) - 1;
-            }
-            __syncthreads();
-            if (s_edge[2] >= 0) break;
+        if (s_ctl[0] == 0) break;  // nothing in flight and the counter is exhausted
+        // q = q1 + step * i in fp64 (reference order of operations), rounded once to fp32
+        for (int t = threadIdx.x; t < TILE * D; t += THREADS) {
+            const int c = t / D, k = t - c * D;
+            const int i = s_idx[c];
+            const int so = s_slot[c] * D + k;
+            sm.q[0][t] = (float)__dadd_rn(e_start[so], __dmul_rn(e_step[so], (double)(i < 0 ? 0 : i)));
         }
-        if (threadIdx.x == 0) {
-            p.flags[e] = s_edge[2] < 0 ? 1 : 0;
-            if (p.first_pos) p.first_pos[e] = s_edge[2];
+        __syncthreads();
+        bool relpen;
+        const float total_pen = process_tile<WARPS>(sm, sm.q[0], D, tol, false, false, &relpen);
+        if (warp == 0) {
+            const unsigned hit = __ballot_sync(FULL, s_idx[lane] >= 0 && total_pen > tol);
+            if (lane < K && s_take[lane] > 0) {
+                const int take = s_take[lane], pref = s_pref[lane];
+                const unsigned range = (take >= 32 ? FULL : ((1u << take) - 1u)) << pref;
+                const unsigned m = hit & range;
+                const int e = s_edge[lane];
+                if (m) {  // first colliding position of this edge: earlier tiles were clean
+                    p.flags[e] = 0;
+                    if (p.first_pos) p.first_pos[e] = s_cur[lane] + (__ffs(m) - 1 - pref);
+                    s_edge[lane] = -1;
+                } else {
+                    const int cur = s_cur[lane] + take;
+                    s_cur[lane] = cur;
+                    if (cur >= s_nmax[lane]) {
+                        p.flags[e] = 1;
+                        if (p.first_pos) p.first_pos[e] = -1;
+                        s_edge[lane] = -1;
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -774,7 +844,7 @@ cudaError_t launch_static_penetration(uint32_t* blob, cudaStream_t st) {
 
 cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
-    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes);
+    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, false);
     const int64_t n_tiles = (p.B + TILE - 1) / TILE;
     if (warps_per_tile(p.world_words) == 4) {
         int grid = grid_for(check_configs_kernel<4>, 128, smem);
@@ -790,7 +860,7 @@ cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st) {
 
 cudaError_t launch_check_edges(const EdgeParams& p, cudaStream_t st) {
     if (p.E <= 0) return cudaSuccess;
-    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes);
+    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, true);
     cudaError_t err = cudaMemsetAsync(p.counter, 0, sizeof(int), st);
     if (err != cudaSuccess) return err;
     if (warps_per_tile(p.world_words) == 4) {
