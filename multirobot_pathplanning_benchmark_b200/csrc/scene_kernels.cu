@@ -61,7 +61,7 @@ __host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_w
     size_t o = 0;
     off[0] = o; o = align16(o + size_t(blob_words) * 4);
     off[1] = o; o = align16(o + size_t(TILE) * D * 4);
-    off[2] = o; o = align16(o + size_t(TILE) * D * 4);
+    off[2] = o; o = align16(o + (edges ? 0 : size_t(TILE) * D * 4));  // second configuration buffer: configuration kernel only
     off[3] = o; o = align16(o + size_t(world_words) * TILE * 4);
     off[4] = o; o = align16(o + size_t(2) * TILE * 4);
     off[5] = o; o = align16(o + size_t(MAX_WARPS) * 64 * 4);
@@ -661,20 +661,28 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(E
     int* s_pref = sm.misc + 5 * K;
     int* s_idx = sm.misc + 8 * K;        // [32] interpolation index of the lane's sample (-1: idle lane)
     int* s_slot = s_idx + 32;            // [32] slot the lane's sample belongs to
-    int* s_ctl = s_slot + 32;            // [0] samples in this tile, [1] edge counter exhausted
+    int* s_ctl = s_slot + 32;            // [0] samples in this tile, [1] edge counter exhausted, [2] samples per edge, last claim
     double* e_start = sm.ed;             // [K][D] q1 (fp64)
     double* e_step = sm.ed + K * D;      // [K][D] (q2 - q1) / (N - 1)
 
     if (threadIdx.x < K) s_edge[threadIdx.x] = -1;
-    if (threadIdx.x == 0) s_ctl[1] = 0;
+    if (threadIdx.x == 0) { s_ctl[1] = 0; s_ctl[2] = TILE; }
     __syncthreads();
 
     for (;;) {
         if (warp == 0) {
-            // ---- refill empty slots: four lanes set up one slot (32 lanes = EDGE_SLOTS x 4) ----
+            // ---- refill: claim only as many edges as it takes to fill the tile's 32 lanes (estimated from the
+            // length of the edges claimed last), so long edges stay one per CTA -- edges parked in slots could not
+            // be picked up by idle CTAs at the end of the batch -- while short ones are claimed by the handful.
+            // Four lanes set up one slot (32 lanes = EDGE_SLOTS x 4).
             for (;;) {
-                const unsigned nm = __ballot_sync(FULL, lane < K && s_edge[lane] < 0);
+                const int have = __reduce_add_sync(FULL, (lane < K && s_edge[lane] >= 0) ? s_nmax[lane] - s_cur[lane] : 0);
+                if (have >= TILE) break;
+                unsigned nm = __ballot_sync(FULL, lane < K && s_edge[lane] < 0);
                 if (!nm || s_ctl[1]) break;
+                const int est = max(s_ctl[2], 1);
+                int want = min((TILE - have + est - 1) / est, __popc(nm));
+                while (__popc(nm) > want) nm &= ~(0x80000000u >> __clz(nm));  // keep the lowest `want` empty slots
                 int base = 0;
                 if (lane == 0) base = atomicAdd(p.counter, __popc(nm));
                 base = __shfl_sync(FULL, base, 0);
@@ -693,6 +701,7 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(E
                 }
                 m = fmax(m, __shfl_xor_sync(FULL, m, 1));
                 m = fmax(m, __shfl_xor_sync(FULL, m, 2));
+                int span = 0;
                 if (mine) {
                     const int N = p.N ? p.N[e] : max(2, (int)__ddiv_rn(m, p.resolution) + 1);
                     const double inv = (double)(N - 1);
@@ -704,13 +713,19 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(E
                             s_N[g] = N;
                             s_nmax[g] = nmax;
                             s_cur[g] = p.n_start;
+                            span = nmax - p.n_start;
                         } else {  // empty window: free, nothing to check
                             p.flags[e] = 1;
                             if (p.first_pos) p.first_pos[e] = -1;
                         }
                     }
                 }
-                if (lane == 0 && (int64_t)base + __popc(nm) >= p.E) s_ctl[1] = 1;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) span += __shfl_xor_sync(FULL, span, o);
+                if (lane == 0) {
+                    s_ctl[2] = span / __popc(nm);  // samples per edge of this claim
+                    if ((int64_t)base + __popc(nm) >= p.E) s_ctl[1] = 1;
+                }
                 __syncwarp();
             }
             // ---- hand the tile's 32 lanes out in slot order ----
@@ -725,12 +740,16 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(E
             const int take = min(rem, TILE - pref);
             if (lane < K) { s_pref[lane] = pref; s_take[lane] = take; }
             const int total = min(__shfl_sync(FULL, incl, K - 1), TILE);
-            __syncwarp();
+            // lane -> slot without a search: bit pref_k marks the first lane of every slot that got lanes; a lane's
+            // slot is the n-th such slot, n = number of marks at or below the lane
+            const bool got = lane < K && take > 0;
+            const unsigned starts = __reduce_or_sync(FULL, got ? 1u << pref : 0u);
+            const unsigned taken = __ballot_sync(FULL, got);
             int slot = 0, i = -1;
             if (lane < total) {
-#pragma unroll
-                for (int k = 1; k < K; k++) slot = (lane >= s_pref[k] && s_take[k] > 0) ? k : slot;
-                const int pos = s_cur[slot] + (lane - s_pref[slot]);
+                const unsigned below = starts & (0xffffffffu >> (31 - lane));  // marks at or below this lane (never empty)
+                slot = (int)__fns(taken, 0, __popc(below));
+                const int pos = s_cur[slot] + lane - (31 - __clz(below));
                 const int N = s_N[slot];
                 i = binary_order_index(N, pos);
                 if (!p.include_endpoints && (i == 0 || i == N - 1)) i = -1;
