@@ -158,14 +158,11 @@ class BatchedPRM:
             self.stats["knn_queries"] += len(V)
             a = np.repeat(np.arange(len(V)), idx.shape[1])
             b = idx.reshape(-1)
-            keep = (b >= 0) & (a < b)                       # undirected: check each candidate edge once
-            rev = (b >= 0) & (a > b)
-            # also keep (a > b) edges whose mirror is not in b's list
-            pairs = set(zip(a[keep].tolist(), b[keep].tolist()))
-            extra = [(y, x) for x, y in zip(a[rev].tolist(), b[rev].tolist()) if (y, x) not in pairs]
-            if extra:
-                pairs.update(extra)
-            e = np.array(sorted(pairs), np.int64).reshape(-1, 2)
+            # undirected: every unordered pair {a, b} that appears in either endpoint's list is checked once
+            valid = (b >= 0) & (a != b)
+            lo, hi = np.minimum(a[valid], b[valid]).astype(np.int64), np.maximum(a[valid], b[valid]).astype(np.int64)
+            key = np.unique(lo * len(V) + hi)               # sorted by (lo, hi)
+            e = np.stack([key // len(V), key % len(V)], axis=1)
             if len(e) == 0:
                 return None
             ok = self._edges_free(slots[i], V[e[:, 0]], V[e[:, 1]])
