@@ -61,13 +61,14 @@ def uniform_configs(lim, B, seed, chunk=4_194_304):
     return out
 
 
-def ncu_traffic(workload, B):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this workload's kernel, from the committed
-    `ncu --set full` capture (profiles/traffic.json, written by scripts/ncu_summary.py output); None if the
-    capture was taken at another batch size."""
+def ncu_capture(workload, B, key):
+    """A per-launch figure of this workload's kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json, filled from scripts/ncu_summary.py output): `dram_bytes` = dram__bytes_read.sum +
+    dram__bytes_write.sum, `executed_fp32_flop` = 2*FFMA + FADD + FMUL thread instructions.  None if the capture
+    was taken at another batch size."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
-        return float(t["dram_bytes"]) if t and int(t["configs"]) == int(B) else None
+        return float(t[key]) if t and int(t["configs"]) == int(B) else None
     except Exception:
         return None
 
@@ -128,11 +129,14 @@ def cpu_baseline(cs, lim, kind_note, budget_s=12.0, edges=None, resolution=None)
     rate = len(probe) / (time.perf_counter() - t)
     n = int(min(max(rate * budget_s, 50_000), 4_000_000))
     q = uniform_configs(lim, n, 0).astype(np.float64)
+    reps = max(1, int(round(budget_s / max(n / rate, 1e-3))))
     t = time.perf_counter()
-    O.check_configs(cs.blob64, q, nthreads=nthreads)
+    for _ in range(reps):
+        O.check_configs(cs.blob64, q, nthreads=nthreads)
     dt = time.perf_counter() - t
-    out = {"value": n / dt, "unit": "configs/s", "cores": nthreads, "kind": "port",
-           "sample": f"{n} uniform configs of the same workload, fp64 C oracle ({kind_note}), {nthreads} OpenMP threads, {dt:.1f} s"}
+    out = {"value": n * reps / dt, "unit": "configs/s", "cores": nthreads, "kind": "port",
+           "sample": f"{reps} passes over {n} uniform configs of the same workload, fp64 C oracle ({kind_note}), "
+                     f"{nthreads} OpenMP threads, {dt:.1f} s"}
     if edges is not None:
         q1, q2 = edges
         m = min(len(q1), 2000)
@@ -324,11 +328,17 @@ def main():
         "frac": achieved / fp32_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, from the committed
         # `ncu --set full` capture (profiles/r1_check_configs_v2_broadphase.txt): 203.5 MB + 17.7 MB
-        "traffic": ncu_traffic(args.workload, B),
+        "traffic": ncu_capture(args.workload, B, "dram_bytes"),
         "algorithmic_bytes": (4 * D + 1) * B,
         "bound_note": "FK + narrowphase is FP32-FMA bound (SURVEY.md 8d); the HBM view is reported under 'hbm'",
         "peak_source": "measured live by mrb200_fp32_probe (MEASURED_PEAKS.json has no FP32-SIMT figure)",
         "algorithmic_flop_per_config": flop_cfg, "kernel_ms": kernel_ms,
+        # what the SIMT pipes really execute after culling / early exit (ncu capture): the algorithmic figure above
+        # counts every collidable pair of the mode and can therefore exceed the pipe's peak
+        "executed": (lambda f: None if f is None else {
+            "fp32_flop_per_launch": f, "tflops": f / (kernel_ms * 1e-3) / 1e12, "frac_of_peak": f / (kernel_ms * 1e-3) / 1e12 / fp32_peak,
+            "source": "profiles/traffic.json (ncu --set full, smsp__sass_thread_inst_executed_op_{ffma,fadd,fmul}_pred_on)"})(
+                ncu_capture(args.workload, B, "executed_fp32_flop")),
         "hbm": {"achieved": bytes_cfg * B / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_cfg * B / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
@@ -362,7 +372,17 @@ def main():
             tc = timed(lambda: be.check_configs(1, qd), 5)
             fr, first = be.check_edges(1, q1, q2, kw2["resolution"])
             te = timed(lambda: be.check_edges(1, q1, q2, kw2["resolution"]), 3)
-            extra[wname] = {"configs_per_s": Bc / tc, "config_free_frac": float(be.check_configs(1, qd).float().mean().item()),
+            # planner-like local edges: every joint moves by at most +-0.2 (mean N ~ 19 at resolution 0.01)
+            El = 131_072
+            l1 = torch.from_numpy(uniform_configs(lim2, El, 10)).to(dev)
+            l1 = l1[be.check_configs(1, l1).bool()].contiguous()
+            step = torch.from_numpy(np.random.RandomState(11).uniform(-0.2, 0.2, tuple(l1.shape)).astype(np.float32)).to(dev)
+            lo_t, hi_t = torch.from_numpy(lim2[0].astype(np.float32)).to(dev), torch.from_numpy(lim2[1].astype(np.float32)).to(dev)
+            l2 = torch.minimum(torch.maximum(l1 + step, lo_t), hi_t).contiguous()
+            lf, _ = be.check_edges(1, l1, l2, kw2["resolution"])
+            tl = timed(lambda: be.check_edges(1, l1, l2, kw2["resolution"]), 3)
+            extra[wname] = {"configs_per_s": Bc / tc, "local_edges_per_s": l1.shape[0] / tl, "local_edge_free_frac": float(lf.float().mean().item()),
+                            "local_edges": int(l1.shape[0]), "config_free_frac": float(be.check_configs(1, qd).float().mean().item()),
                             "edges_per_s": Ew / te, "edge_free_frac": float(fr.float().mean().item()),
                             "edge_resolution": kw2["resolution"], "edges": Ew, "configs": Bc,
                             "algorithmic_flop_per_config": S.algorithmic_flops_per_config(cs2)}
