@@ -360,6 +360,8 @@ def main():
 
         edge_inputs = None
         for wname, (sname, Bw, Ew) in WORKLOADS.items():
+            if wname in STRONG and wname != args.workload:
+                continue  # same scene as its per-GPU sibling
             mk2, kw2 = SCENES[sname]
             sc2 = mk2()
             cs2 = S.compile_blob(sc2, kw2["tol"])
