@@ -391,6 +391,30 @@ def main():
             if wname == args.workload:
                 edge_inputs = (q1.cpu().numpy(), q2.cpu().numpy())
             del qd, q1, q2
+        # modes of the default scene: start mode, a box held by a1, a box held by a2, and a mode-mixed batch
+        # (the reference's benchmark draws a random reachable mode per sample, scripts/show_problems.py:177-181)
+        if scene_name == "box_rearrangement":
+            from multirobot_pathplanning_benchmark_b200.env import SceneModel
+            model = SceneModel(sc, kw["tol"], kw["resolution"], device=None)
+            base_slot = model.slot_for(())
+            cand = uniform_configs(lim, 8192, 21)
+            okc = model.check_configs(base_slot, torch.from_numpy(cand).to(dev)).cpu().numpy().astype(bool)
+            q_att = cand[int(np.argmax(okc))].astype(np.float64)
+            mslots = {"start": base_slot,
+                      "a1_holds_obj11": model.slot_for(("a1",), [("a1_ur_vacuum", "obj11", q_att)]),
+                      "a2_holds_obj00": model.slot_for(("a2",), [("a2_ur_vacuum", "obj00", q_att)])}
+            qm = torch.from_numpy(uniform_configs(lim, 2_097_152, 22)).to(dev)
+            modes = {}
+            for mname, mslot in mslots.items():
+                tm = timed(lambda: model.check_configs(mslot, qm), 5)
+                modes[mname] = {"configs_per_s": qm.shape[0] / tm, "free_frac": float(model.check_configs(mslot, qm).float().mean().item()),
+                                "collidable_pairs": int(sum(model.compiled(mslot).pair_counts))}
+            third = qm.shape[0] // 3
+            parts = [qm[i * third:(i + 1) * third].contiguous() for i in range(3)]
+            tmix = timed(lambda: [model.check_configs(sl_, p_) for sl_, p_ in zip(mslots.values(), parts)], 5)
+            modes["mixed_thirds"] = {"configs_per_s": 3 * third / tmix}
+            extra["modes_box_rearrangement"] = modes
+            del qm, parts
         # BASELINE config 4: batched k-NN for PRM/EIT graph building, 100k samples of one mode, D = 24
         from multirobot_pathplanning_benchmark_b200 import knn as K
         Nk, Dk, kk = 100_000, 24, K.prm_k_star(100_000, 24)

@@ -27,6 +27,11 @@ for k, v in x.items():
     if "configs_per_s" in v:
         print(f"| {k} | {v['configs_per_s']:.4g} | {v['edges_per_s']:.4g} | {v.get('local_edges_per_s', float('nan')):.4g} | {v['config_free_frac']:.3f} | "
               f"{v['edge_free_frac']:.4f} | {v.get('local_edge_free_frac', float('nan')):.3f} |")
+m = x.get("modes_box_rearrangement")
+if m:
+    print("\n* modes of the dual-arm scene (2 097 152 configs): " + "; ".join(
+        f"{k} {v['configs_per_s']:.4g}/s" + (f" ({v['collidable_pairs']} pairs, {v['free_frac']:.3f} free)" if "free_frac" in v else "")
+        for k, v in m.items()))
 k = x.get("knn_box_stacking_100k")
 if k:
     print(f"\n* k-NN {k['N']} x {k['Q']}, D={k['D']}, 4 robots, k={k['k']}, {k['metric']}: tcgen05 path {k['tensor_ms']:.1f} ms "

@@ -1,0 +1,22 @@
+"""Batch-native PRM (planner.py) on the GPU: the CUDA backend and the CPU oracle backend answer the same batch
+calls, so with the same seed the planner must find the same plan (BASELINE metric: time-to-first-solution)."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("scene,n0,t0", [("2d_handover", 400, 50), ("box_rearrangement", 1500, 150)])
+def test_same_seed_same_plan_on_both_backends(cuda_lib, scene, n0, t0):
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import ttfs
+    gpu = ttfs.run(scene, "b200", 0, n0, t0, 120)
+    cpu = ttfs.run(scene, "cpu", 0, n0, t0, 300)
+    assert gpu["solved"] and cpu["solved"]
+    assert abs(gpu["cost"] - cpu["cost"]) < 1e-9
+    for k in ("config_checks", "edge_checks", "knn_queries", "rounds"):
+        assert gpu[k] == cpu[k], k
+    assert gpu["time_s"] < cpu["time_s"]
