@@ -78,6 +78,9 @@ class CudaDevice:
     def to_numpy(x):
         return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
 
+    def __deepcopy__(self, memo):
+        return self  # a handle to device-resident, append-only state: copies of an environment share it
+
 
 # ----------------------------------------------------------------------------------------------
 # speculative batching behind the single-query API
@@ -190,6 +193,13 @@ class SceneModel:
             self._compiled[slot] = cs
             self._scenes[slot] = sc
         return self._slots[key]
+
+    def __deepcopy__(self, memo):
+        """The reference deep-copies its environments, one per planner run (P/scripts/run_experiment.py:276,420;
+        custom copies in P/problems/rai_base_env.py:337-369).  A SceneModel is a cache of compiled kinematic trees
+        keyed by their relink chain -- a pure function of the key, living in slots of one device handle -- so
+        copies share it; per-environment state (current mode, speculation cache, sampler) lives in B200Env."""
+        return self
 
     def compiled(self, slot: int) -> CompiledScene:
         return self._compiled[slot]
@@ -523,6 +533,9 @@ if HAVE_REFERENCE:
             from .backend import AbstractBackend
             self.torch = torch
             self.be = AbstractBackend(n_agents, dim, radii, spheres, rects_minmax)
+
+        def __deepcopy__(self, memo):
+            return self  # immutable device-side scene: environment copies share it
 
         def check_configs(self, q):
             t = self.torch

@@ -207,3 +207,25 @@ def test_speculative_sample_block_serves_rejection_sampling(envmod):
     q[0] = q[0] + 0.01
     assert env.is_collision_free(q, env.start_mode) == plain.is_collision_free(q, plain.start_mode)
     assert dev.calls["configs"] == 2
+
+
+def test_deepcopy_shares_the_device_and_keeps_private_state(envmod):
+    """the reference copies its environment per planner run (run_experiment.py:276, rai_base_env.py:337-369)"""
+    import copy
+    dev = OracleSceneDevice()
+    env = envmod.b200_two_dim_handover(device=dev)
+    q = env.sample_config_uniform_in_limits()
+    env.is_collision_free(q, env.start_mode)
+    env2 = copy.deepcopy(env)
+    assert env2.model is env.model and env2.model.device is dev
+    assert env2.spec_cache is not env.spec_cache and env2.tasks is not env.tasks
+    np.random.seed(5)
+    a = [env.sample_config_uniform_in_limits().state().copy() for _ in range(3)]
+    np.random.seed(5)
+    b = [env2.sample_config_uniform_in_limits().state().copy() for _ in range(3)]
+    assert len(a) == len(b) == 3  # both samplers work after the copy (the generator itself is not copied)
+    for m, qq in walk_modes(env)[:3]:
+        m2 = [mm for mm, _ in walk_modes(env2) if mm.task_ids == m.task_ids][0]
+        assert env.is_collision_free(qq, m) == env2.is_collision_free(qq, m2)
+    path, _ = run_planner(env2, "prm", 1, max_time=60)
+    assert path is not None and env2.is_valid_plan(path)
