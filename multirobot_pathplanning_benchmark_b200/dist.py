@@ -47,3 +47,28 @@ def sharded_map(fn: Callable[[int, int], torch.Tensor], n_total: int, group=None
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     s, e = shard_range(n_total, rank, world)
     return gather_rows(fn(s, e), n_total, group)
+
+
+def gather_csr(offsets: torch.Tensor, indices: torch.Tensor, n_rows_total: int, group=None):
+    """All-gather of ragged per-row lists (r-disc neighbour search sharded by query rows): every rank
+    holds the CSR (offsets [rows_local + 1], indices) of its shard_range block; returns the CSR of all rows.
+    Two exchanges: the per-row counts, then the indices padded to the longest shard."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return offsets, indices
+    counts = (offsets[1:] - offsets[:-1]).to(torch.int64)
+    all_counts = gather_rows(counts, n_rows_total, group)
+    sizes = shard_sizes(n_rows_total, world)
+    row_starts = [0]
+    for s_ in sizes:
+        row_starts.append(row_starts[-1] + s_)
+    per_rank = [int(all_counts[row_starts[r]:row_starts[r + 1]].sum().item()) for r in range(world)]
+    width = max(max(per_rank), 1)
+    pad = torch.zeros(width, dtype=indices.dtype, device=indices.device)
+    pad[:indices.shape[0]] = indices
+    out = torch.empty(world * width, dtype=indices.dtype, device=indices.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    all_idx = torch.cat([out[r * width:r * width + n] for r, n in enumerate(per_rank)])
+    all_off = torch.zeros(n_rows_total + 1, dtype=torch.int64, device=offsets.device)
+    all_off[1:] = torch.cumsum(all_counts, 0)
+    return all_off, all_idx

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from multirobot_pathplanning_benchmark_b200 import scene as S
-from multirobot_pathplanning_benchmark_b200.dist import gather_rows, shard_range, shard_sizes, sharded_map
+from multirobot_pathplanning_benchmark_b200.dist import gather_csr, gather_rows, shard_range, shard_sizes, sharded_map
 from multirobot_pathplanning_benchmark_b200.scenes import SCENES
 
 
@@ -64,3 +64,38 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
 def test_gather_rows_single_process_is_identity():
     x = torch.arange(10)
     assert torch.equal(gather_rows(x, 10), x)
+
+
+def _radius_csr(queries, corpus, r):
+    """reference-style r-disc rows (np.where order, prm_graph.py:479-500) as CSR"""
+    from oracle import oracle_abstract as OA
+    sl = np.array([[0, 2], [2, 4]])
+    rows = [np.nonzero(OA.batch_config_dist(q, corpus, sl, "max_euclidean") < r)[0] for q in queries]
+    off = np.zeros(len(rows) + 1, np.int64)
+    off[1:] = np.cumsum([len(x) for x in rows])
+    return off, (np.concatenate(rows) if rows else np.zeros(0, np.int64)).astype(np.int32)
+
+
+def _csr_worker(rank, world, port, Q, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    corpus = np.random.RandomState(2).uniform(-2, 2, (300, 4))
+    queries = corpus[:Q]
+    s, e = shard_range(Q, rank, world)
+    off, idx = _radius_csr(queries[s:e], corpus, 0.9)
+    goff, gidx = gather_csr(torch.from_numpy(off), torch.from_numpy(idx), Q)
+    if rank == 1:
+        np.savez(out_path, off=goff.numpy(), idx=gidx.numpy())
+    dist.destroy_process_group()
+
+
+def test_ragged_radius_rows_gather_across_two_ranks(tmp_path):
+    Q = 101
+    out = str(tmp_path / "csr.npz")
+    mp.spawn(_csr_worker, args=(2, 29731 + os.getpid() % 200, Q, out), nprocs=2, join=True)
+    got = np.load(out)
+    corpus = np.random.RandomState(2).uniform(-2, 2, (300, 4))
+    off, idx = _radius_csr(corpus[:Q], corpus, 0.9)
+    assert np.array_equal(got["off"], off) and np.array_equal(got["idx"], idx)
+    assert idx.size > Q  # every row holds at least itself, most hold more
