@@ -79,6 +79,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr)
         : "memory");
 }
+// 16 consecutive FP32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor: K-major, no swizzle, LBO = 128 B, SBO = 256 B, version 1 (sm_100)
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: 8 warps; thread = (query row, half); 32-column chunks alternate between halves =====
+        // ===== epilogue: 8 warps; thread = (query row, half); 16-column chunks alternate between halves =====
         const int quarter = warp & 3, half = (warp - 4) >> 2;
         const int r_in_tile = quarter * 32 + lane;
         const int hslot = half * TC_TM + r_in_tile;            // this thread's heap / staging column
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         int* si = stg_i + hslot;
         int staged = 0;
         float thr = 3.0e38f;
-        const int chunks_per_tile = tn >> 5;
+        const int chunks_per_tile = tn >> 4;   // 16-column chunks: the loads of up to four robots' accumulators fly together
         // every lane pushes its staged candidates into its own heap at the same time: the sift loops of the 32
         // lanes run side by side instead of one lane at a time
         auto flush = [&]() {
@@ -269,32 +280,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             mbar_wait(&tm_full[buf], use & 1);
             tc_fence_after();
             const int64_t col0 = (t0 + t) * tn;
-            for (int ci = 0; ci < chunks_per_tile; ci++) {
-                if (((t * chunks_per_tile + ci) & 1) != half) continue;   // warp-uniform
-                const int c = ci << 5;
-                float v[32];
+            // the two halves take alternate chunks (chunks_per_tile is even, so the parity of a chunk is that of ci)
+            for (int ci = half; ci < chunks_per_tile; ci += 2) {
+                const int c = ci << 4;
+                float v[16], b1[16], b2[16], b3[16];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * buf_cols + c);
-                tmem_ld32(taddr, v);
+                // issue every accumulator's load before the one wait (n_acc is uniform across the CTA)
+                tmem_ld16(taddr, v);
+                if (n_acc > 1) tmem_ld16(taddr + (uint32_t)tn, b1);
+                if (n_acc > 2) tmem_ld16(taddr + (uint32_t)(2 * tn), b2);
+                if (n_acc > 3) tmem_ld16(taddr + (uint32_t)(3 * tn), b3);
                 tmem_ld_wait();
-                for (int a = 1; a < n_acc; a++) {
-                    float u[32];
-                    tmem_ld32(taddr + (uint32_t)(a * tn), u);
-                    tmem_ld_wait();
+                if (n_acc == 2) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], u[j]);
+                    for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], b1[j]);
+                } else if (n_acc == 3) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[j] = fmaxf(fmaxf(v[j], b1[j]), b2[j]);   // three-input max
+                } else if (n_acc >= 4) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[j] = fmaxf(fmaxf(v[j], b1[j]), fmaxf(b2[j], b3[j]));
                 }
+                for (int a = 4; a < n_acc; a += 2) {  // more than four robots: two more at a time
+                    tmem_ld16(taddr + (uint32_t)(a * tn), b1);
+                    if (a + 1 < n_acc) tmem_ld16(taddr + (uint32_t)((a + 1) * tn), b2);
+                    tmem_ld_wait();
+                    if (a + 1 < n_acc) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = fmaxf(fmaxf(v[j], b1[j]), b2[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], b1[j]);
+                    }
+                }
+                // after warm-up hardly any chunk holds a candidate: one min tree + one compare per lane, and the
+                // per-column mask only when some lane of the warp needs it
+                float lo8[8], lo4[4];
+#pragma unroll
+                for (int j = 0; j < 8; j++) lo8[j] = fminf(v[j], v[8 + j]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) lo4[j] = fminf(lo8[j], lo8[4 + j]);
+                const float lo = fminf(fminf(lo4[0], lo4[1]), fminf(lo4[2], lo4[3]));
+                if (!__any_sync(0xffffffffu, lo < thr)) continue;
                 uint32_t mask = 0u;
 #pragma unroll
-                for (int j = 0; j < 32; j++) mask |= (v[j] < thr ? 1u : 0u) << j;
+                for (int j = 0; j < 16; j++) mask |= (v[j] < thr ? 1u : 0u) << j;
                 while (mask) {  // a handful of candidates per chunk and warp
                     const int j = __ffs(mask) - 1;
                     mask &= mask - 1u;
-                    // v[j] with a run-time j: five levels of selects keep v in registers
-                    float s16[16], s8[8], s4[4], s2[2];
+                    // v[j] with a run-time j: four levels of selects keep v in registers
+                    float s8[8], s4[4], s2[2];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) s16[i] = (j & 16) ? v[16 + i] : v[i];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) s8[i] = (j & 8) ? s16[8 + i] : s16[i];
+                    for (int i = 0; i < 8; i++) s8[i] = (j & 8) ? v[8 + i] : v[i];
 #pragma unroll
                     for (int i = 0; i < 4; i++) s4[i] = (j & 4) ? s8[4 + i] : s8[i];
 #pragma unroll

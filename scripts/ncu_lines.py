@@ -8,6 +8,7 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(io.StringIO(out)))
 hdr, data = rows[1], rows[2:]
 ia, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
+stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "multirobot_pathplanning_benchmark_b200", "libmrb200.so")], cwd=tmp, capture_output=True)
 dis = None
@@ -29,6 +30,7 @@ for l in dis.split("\n"):
         addr2line[int(m.group(1), 16)] = cur
 base = int(data[0][0], 16)
 agg, samp, tot = collections.Counter(), collections.Counter(), 0
+stl = collections.defaultdict(collections.Counter)
 for r in data:
     try:
         a = int(r[0], 16) - base
@@ -38,6 +40,8 @@ for r in data:
     n = int(r[ia] or 0)
     agg[fl] += n
     samp[fl] += int(r[isamp] or 0)
+    for i in stall_cols:
+        stl[fl][hdr[i][6:]] += int(r[i] or 0)
     tot += n
 print("total warp instructions", tot, "sass lines", len(data))
 srcs = {}
@@ -48,4 +52,5 @@ for fl, n in agg.most_common(top):
         srcs.setdefault(path[0], open(path[0]).read().split("\n"))
         if 0 < fl[1] <= len(srcs[path[0]]):
             txt = srcs[path[0]][fl[1] - 1].strip()[:90]
-    print(f"{fl[0]:20s} {fl[1]:4d} {n / tot * 100:5.1f}%  smp {samp[fl]:6d}  {txt}")
+    why = " ".join(f"{k}:{v * 100 // max(samp[fl], 1)}" for k, v in stl[fl].most_common(3))
+    print(f"{fl[0]:20s} {fl[1]:4d} {n / tot * 100:5.1f}%  smp {samp[fl]:6d}  [{why}]  {txt[:60]}")
