@@ -286,7 +286,6 @@ def main():
     launches = launch_count() - l0
     total_ms = max_over_ranks(t0.elapsed_time(t1))
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
-    clk = clocks.stop() if rank == 0 else None
     value = world * B * args.steps / (total_ms * 1e-3)
     free_frac = float(flags.float().mean().item())
 
@@ -305,6 +304,7 @@ def main():
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+    clk = clocks.stop() if rank == 0 else None   # sampled over both timed regions (resident and end-to-end)
     assert torch.equal(out_host.to(dev), flags), "host-API flags differ from the device-resident run"
 
     if rank != 0:
@@ -391,6 +391,30 @@ def main():
             if wname == args.workload:
                 edge_inputs = (q1.cpu().numpy(), q2.cpu().numpy())
             del qd, q1, q2
+        # BASELINE config 1 (abstract.test, D = 4): micro-batches on the fp64 abstract kernels, bit-exact with the reference
+        from multirobot_pathplanning_benchmark_b200.backend import AbstractBackend
+        ab = AbstractBackend(2, 2, [0.1, 0.1], spheres=[([0.0, 0.0], 0.2)], rects_minmax=[([-0.25, 0.15], [0.25, 0.65])], device=dev)
+        rs = np.random.RandomState(3)
+        qa = torch.from_numpy(rs.uniform(-2, 2, (1_000_000, 4))).to(dev)
+        ea, eb = torch.from_numpy(rs.uniform(-2, 2, (100_000, 4))).to(dev), torch.from_numpy(rs.uniform(-2, 2, (100_000, 4))).to(dev)
+        ta = timed(lambda: ab.check_configs(qa), 5)
+        tea = timed(lambda: ab.check_edges(ea, eb, 0.01), 3)
+        abstract = {"configs": 1_000_000, "configs_per_s": 1_000_000 / ta, "edges": 100_000, "edges_per_s": 100_000 / tea,
+                    "resolution": 0.01, "free_frac": float(ab.check_configs(qa).float().mean().item())}
+        if not args.no_cpu:
+            from oracle import oracle_abstract as OA
+            osc = OA.AbstractScene.abstract_test()
+            qh = qa[:200_000].cpu().numpy()
+            t = time.perf_counter()
+            of = osc.batch_flags(qh)
+            abstract["cpu_port_vectorised_configs_per_s_1core"] = len(qh) / (time.perf_counter() - t)
+            t = time.perf_counter()
+            for row in qh[:2000]:
+                osc.is_collision_free(row)
+            abstract["cpu_port_per_call_configs_per_s_1core"] = 2000 / (time.perf_counter() - t)
+            abstract["flags_identical"] = bool(np.array_equal(of, ab.check_configs(qa[:200_000]).cpu().numpy()))
+        extra["abstract_test"] = abstract
+        del qa, ea, eb
         # modes of the default scene: start mode, a box held by a1, a box held by a2, and a mode-mixed batch
         # (the reference's benchmark draws a random reachable mode per sample, scripts/show_problems.py:177-181)
         if scene_name == "box_rearrangement":

@@ -24,9 +24,15 @@ x = d.get("extra", {})
 print("| scene | configs/s | edges/s, uniform endpoints | edges/s, local (±0.2 per joint) | free configs | free uniform edges | free local edges |")
 print("|---|---|---|---|---|---|---|")
 for k, v in x.items():
-    if "configs_per_s" in v:
+    if "config_free_frac" in v:
         print(f"| {k} | {v['configs_per_s']:.4g} | {v['edges_per_s']:.4g} | {v.get('local_edges_per_s', float('nan')):.4g} | {v['config_free_frac']:.3f} | "
               f"{v['edge_free_frac']:.4f} | {v.get('local_edge_free_frac', float('nan')):.3f} |")
+a = x.get("abstract_test")
+if a:
+    print(f"\n* abstract.test (D=4, fp64, bit-exact): {a['configs_per_s']:.4g} configs/s, {a['edges_per_s']:.4g} edges/s at resolution {a['resolution']}"
+          + (f"; CPU port on one core: {a['cpu_port_vectorised_configs_per_s_1core']:.4g} configs/s vectorised, "
+             f"{a['cpu_port_per_call_configs_per_s_1core']:.4g}/s one call per configuration like the reference's planners; flags identical: {a['flags_identical']}"
+             if "flags_identical" in a else ""))
 m = x.get("modes_box_rearrangement")
 if m:
     print("\n* modes of the dual-arm scene (2 097 152 configs): " + "; ".join(
