@@ -167,7 +167,7 @@ def run_reference(args):
     O.check_configs(cs.blob64, probe, nthreads=nthreads)
     rate = len(probe) / (time.perf_counter() - t)
     total_steps = args.steps + args.warmup
-    n = int(min(max(rate * 60.0 / max(total_steps, 1), 20_000), B))  # whole run ~1 minute
+    n = int(min(max(rate * args.ref_seconds / max(total_steps, 1), 2_000), B))  # whole run ~ref_seconds
     q = uniform_configs(lim, n, 0).astype(np.float64)
     for _ in range(args.warmup):
         O.check_configs(cs.blob64, q, nthreads=nthreads)
@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=list(WORKLOADS))
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary scenes / edge rates")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: CPU time budget of the whole run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:  # secondary scenes and the CPU leg are N = 1 only

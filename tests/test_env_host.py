@@ -229,3 +229,31 @@ def test_deepcopy_shares_the_device_and_keeps_private_state(envmod):
         assert env.is_collision_free(qq, m) == env2.is_collision_free(qq, m2)
     path, _ = run_planner(env2, "prm", 1, max_time=60)
     assert path is not None and env2.is_valid_plan(path)
+
+
+def test_reference_shortcutter_on_batched_path_checks(reference, envmod):
+    """the reference's robot_mode_shortcut (P/planners/shortcutting.py:87-245) validates every
+    candidate with env.is_path_collision_free; on B200Env that is one vertex batch + one edge batch per mode.
+    Same seeds -> same shortcut decisions and the same final path as with the reference's own per-query loop."""
+    from multi_robot_multi_goal_planning.planners.shortcutting import robot_mode_shortcut
+    from multi_robot_multi_goal_planning.problems.planning_env import BaseProblem
+    results = {}
+    for batched in (True, False):
+        dev = OracleSceneDevice()
+        env = envmod.b200_two_dim_handover(device=dev, speculate=False)
+        path, _ = run_planner(env, "prm", 1, max_time=60)
+        assert path is not None
+        if not batched:  # the reference's own loop over single edge / configuration queries
+            env.is_path_collision_free = lambda p, **kw: BaseProblem.is_path_collision_free(env, p, **kw)
+        before = dict(dev.calls)
+        np.random.seed(7)
+        random.seed(7)
+        new_path, (costs, _) = robot_mode_shortcut(env, path, max_iter=40, resolution=env.collision_resolution,
+                                                   tolerance=env.collision_tolerance)
+        calls = {k: dev.calls[k] - before[k] for k in dev.calls}
+        results[batched] = (np.stack([s.q.state() for s in new_path]), costs[-1], calls)
+    (pa, ca, calls_b), (pb, cb, calls_r) = results[True], results[False]
+    assert pa.shape == pb.shape and np.array_equal(pa, pb) and ca == cb
+    assert ca < results[True][1] + 1e-12
+    print("device calls during shortcutting, batched / per-query:", calls_b, calls_r)
+    assert calls_b["edges"] * 3 < calls_r["edges"]
