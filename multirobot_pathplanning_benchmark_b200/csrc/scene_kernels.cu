@@ -722,6 +722,7 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(E
                 }
 #pragma unroll
                 for (int o = 16; o; o >>= 1) span += __shfl_xor_sync(FULL, span, o);
+                __syncwarp();  // every lane has read s_ctl[1], s_ctl[2] of this round
                 if (lane == 0) {
                     s_ctl[2] = span / __popc(nm);  // samples per edge of this claim
                     if ((int64_t)base + __popc(nm) >= p.E) s_ctl[1] = 1;
