@@ -469,12 +469,15 @@ def main():
         import ttfs
         ttfs.run("2d_handover", "b200", 99, 200, 30, 30)   # warm-up
         tt = {}
-        for sname, n0, t0, cpu_seeds in (("2d_handover", 500, 60, 3), ("box_rearrangement", 4000, 400, 1), ("box_stacking", 6000, 600, 1)):
-            gpu_runs = [ttfs.run(sname, "b200", seed, n0, t0, 120) for seed in range(3)]
-            entry = {"samples_per_mode": n0, "b200_median_s": float(np.median([r["time_s"] for r in gpu_runs])),
-                     "b200_runs": gpu_runs}
+        # 2d_handover: pick / handover / place sequence (6 modes); box_rearrangement: 2 pick-and-place moves with the
+        # vacuum tools (5 modes); box_stacking: the four arms stack 4 boxes (9 modes); keyframes from problems.py
+        for sname, n0, t0, cpu_seeds, n_moves in (("2d_handover", 500, 60, 3, 0), ("box_rearrangement", 2000, 200, 1, 2),
+                                                  ("box_stacking", 3000, 300, 1, 4)):
+            gpu_runs = [ttfs.run(sname, "b200", seed, n0, t0, 120, n_moves=n_moves) for seed in range(3)]
+            entry = {"samples_per_mode": n0, "pick_place_moves": n_moves, "modes": 6 if sname == "2d_handover" else 2 * n_moves + 1,
+                     "b200_median_s": float(np.median([r["time_s"] for r in gpu_runs])), "b200_runs": gpu_runs}
             if not args.no_cpu:
-                cpu_runs = [ttfs.run(sname, "cpu", seed, n0, t0, 240) for seed in range(cpu_seeds)]
+                cpu_runs = [ttfs.run(sname, "cpu", seed, n0, t0, 600, n_moves=n_moves) for seed in range(cpu_seeds)]
                 entry["cpu_port_median_s"] = float(np.median([r["time_s"] for r in cpu_runs]))
                 entry["cpu_runs"] = cpu_runs
                 entry["same_plans"] = all(abs(a["cost"] - b["cost"]) < 1e-9 for a, b in zip(gpu_runs, cpu_runs))

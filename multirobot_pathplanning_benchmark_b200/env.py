@@ -490,6 +490,31 @@ if HAVE_REFERENCE:
             BaseModeLogic.__init__(self)
             self.prev_mode = None
 
+    def _manipulation_env(scene_name: str, default_moves: int):
+        """Pick / place sequence problems on the named arm scenes: B200 counterparts of rai.box_rearrangement
+        (rai_envs.py:1454-1594) and rai.box_stacking (rai_envs.py:1916-1966).  Same scene, same kind of task list
+        (pick: object re-parented to the tool frame; place: back to the table; final task: all robots home); the
+        goal keyframes come from problems.py / keyframes.py instead of rai's KOMO (see there)."""
+
+        class _Env(SequenceMixin, B200Env):
+            def __init__(self, device=None, speculate: bool = True, n_moves: int = default_moves, seed: int = 0):
+                from .problems import manipulation_tasks
+                mk, kw = SCENES[scene_name]
+                B200Env.__init__(self, mk(), kw["tol"], kw["resolution"], device=device, speculate=speculate)
+                self.manipulating_env = True
+                specs = manipulation_tasks(scene_name, self.model, n_moves=n_moves, seed=seed)
+                self.tasks = [Task(t.name, list(t.robots), SingleGoal(t.goal), type=t.type,
+                                   frames=None if t.frames is None else list(t.frames)) for t in specs]
+                self.sequence = self._make_sequence_from_names([t.name for t in specs])
+                BaseModeLogic.__init__(self)
+                self.prev_mode = None
+
+        _Env.__name__ = f"b200_{scene_name}"
+        return _Env
+
+    b200_box_rearrangement = register("b200.box_rearrangement")(_manipulation_env("box_rearrangement", 4))
+    b200_box_stacking = register("b200.box_stacking")(_manipulation_env("box_stacking", 4))
+
     def _goto_env(scene_name: str, seed: int):
         """Geometry of a named scene with plain goto tasks: every robot moves to a sampled collision-free
         goal, then all return home.  (The reference's pick / place keyframes come from rai's KOMO.)"""

@@ -6,6 +6,7 @@ sys.path.insert(0, ".")
 from multirobot_pathplanning_benchmark_b200.env import SceneModel, CudaDevice
 from multirobot_pathplanning_benchmark_b200.planner import BatchedPRM, SeqTask
 from multirobot_pathplanning_benchmark_b200.scenes import SCENES
+from multirobot_pathplanning_benchmark_b200 import problems as P
 
 
 def handover_tasks(start):
@@ -35,7 +36,7 @@ def goto_tasks(model, sc, seed):
     return tasks
 
 
-def run(scene_name, backend, seed, n0, t0, max_time):
+def run(scene_name, backend, seed, n0, t0, max_time, goto=False, n_moves=4):
     mk, kw = SCENES[scene_name]
     sc = mk()
     if backend == "b200":
@@ -61,7 +62,13 @@ def run(scene_name, backend, seed, n0, t0, max_time):
                 idx = OA.knn_indices(OA.batch_config_dist(row, c, sl, metric), k)
                 out[i, :len(idx)] = idx
             return out
-    tasks = handover_tasks(sc.home()) if scene_name == "2d_handover" else goto_tasks(model, sc, 100 + seed)
+    if scene_name == "2d_handover":
+        tasks = handover_tasks(sc.home())
+    elif scene_name in P.PROBLEMS and not goto:
+        # pick / place sequence with held objects (keyframes by numerical IK, checked by this backend)
+        tasks = [SeqTask(list(t.robots), t.goal, t.frames) for t in P.manipulation_tasks(scene_name, model, n_moves=n_moves, seed=0)]
+    else:
+        tasks = goto_tasks(model, sc, 100 + seed)
     prm = BatchedPRM(model, tasks, sc.home(), knn, seed=seed, samples_per_mode=n0, transitions_per_mode=t0)
     res = prm.plan(max_time=max_time)
     return {"solved": res.path is not None, "time_s": res.time_s, "cost": res.cost, **res.stats}

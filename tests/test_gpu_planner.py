@@ -9,12 +9,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("scene,n0,t0", [("2d_handover", 400, 50), ("box_rearrangement", 1500, 150)])
-def test_same_seed_same_plan_on_both_backends(cuda_lib, scene, n0, t0):
+@pytest.mark.parametrize("scene,n0,t0,n_moves", [("2d_handover", 400, 50, 0), ("box_rearrangement", 1000, 100, 1), ("box_stacking", 800, 80, 1)])
+def test_same_seed_same_plan_on_both_backends(cuda_lib, scene, n0, t0, n_moves):
+    """pick / place sequences with held objects (problems.py); the keyframes themselves are solved against each
+    backend's own collision answers and must coincide too"""
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import ttfs
-    gpu = ttfs.run(scene, "b200", 0, n0, t0, 120)
-    cpu = ttfs.run(scene, "cpu", 0, n0, t0, 300)
+    gpu = ttfs.run(scene, "b200", 0, n0, t0, 120, n_moves=n_moves)
+    cpu = ttfs.run(scene, "cpu", 0, n0, t0, 300, n_moves=n_moves)
     assert gpu["solved"] and cpu["solved"]
     assert abs(gpu["cost"] - cpu["cost"]) < 1e-9
     for k in ("config_checks", "edge_checks", "knn_queries", "rounds"):
