@@ -15,6 +15,7 @@ def test_same_seed_same_plan_on_both_backends(cuda_lib, scene, n0, t0, n_moves):
     backend's own collision answers and must coincide too"""
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import ttfs
+    ttfs.run("2d_handover", "b200", 99, 200, 30, 30)   # warm-up: CUDA context, module load
     gpu = ttfs.run(scene, "b200", 0, n0, t0, 120, n_moves=n_moves)
     cpu = ttfs.run(scene, "cpu", 0, n0, t0, 300, n_moves=n_moves)
     assert gpu["solved"] and cpu["solved"]
