@@ -23,10 +23,11 @@ from .scenes import SCENES
 
 try:  # the reference package (optional at import time)
     from multi_robot_multi_goal_planning.problems.planning_env import (  # type: ignore
-        BaseModeLogic, BaseProblem, Mode, SequenceMixin, State, Task, ProblemSpec, AgentType, ConstraintType,
+        BaseModeLogic, BaseProblem, DependencyGraphMixin, Mode, SequenceMixin, State, Task, ProblemSpec, AgentType, ConstraintType,
         ManipulationType, DependencyType, DynamicsType, GoalType, SafePoseType, generate_binary_search_indices)
     from multi_robot_multi_goal_planning.problems.core.configuration import (  # type: ignore
         NpConfiguration, batch_config_cost, config_cost, config_dist)
+    from multi_robot_multi_goal_planning.problems.core.dependency_graph import DependencyGraph  # type: ignore
     from multi_robot_multi_goal_planning.problems.core.goals import GoalSet, SingleGoal  # type: ignore
     from multi_robot_multi_goal_planning.problems.core.registry import register  # type: ignore
     HAVE_REFERENCE = True
@@ -514,6 +515,35 @@ if HAVE_REFERENCE:
 
     b200_box_rearrangement = register("b200.box_rearrangement")(_manipulation_env("box_rearrangement", 4))
     b200_box_stacking = register("b200.box_stacking")(_manipulation_env("box_stacking", 4))
+
+    @register("b200.dep_mobile_wall_four")
+    class b200_dep_mobile_wall_four(DependencyGraphMixin, B200Env):
+        """B200 counterpart of rai.dep_mobile_wall_four (rai_envs.py:2206-2276): every mobile manipulator carries the two
+        boxes of its wall column to the goal wall; a robot's tasks are chained, robots are independent of each other,
+        the terminal task depends on all of them (same dependency graph as :2224-2258)."""
+
+        def __init__(self, device=None, speculate: bool = True, num_robots: int = 4, seed: int = 0):
+            from .problems import manipulation_tasks
+            mk, kw = SCENES["mobile_wall_four"]
+            B200Env.__init__(self, mk(num_robots) if num_robots != 4 else mk(), kw["tol"], kw["resolution"], device=device,
+                             speculate=speculate)
+            self.manipulating_env = True
+            specs = manipulation_tasks("mobile_wall_four", self.model, n_moves=2 * num_robots, seed=seed)
+            self.graph = DependencyGraph()
+            self.tasks = []
+            prev = {}
+            for t in specs[:-1]:
+                r = t.robots[0]
+                self.tasks.append(Task(t.name, [r], SingleGoal(t.goal), type=t.type, frames=list(t.frames)))
+                if r in prev:
+                    self.graph.add_dependency(t.name, prev[r])
+                prev[r] = t.name
+            for r in self.robots:
+                self.graph.add_dependency("terminal", prev[r])
+            self.tasks.append(Task("terminal", list(self.robots), SingleGoal(self.start_pos.state())))
+            BaseModeLogic.__init__(self)
+            self.prev_mode = None
+            self.spec.dependency = DependencyType.UNORDERED
 
     def _goto_env(scene_name: str, seed: int):
         """Geometry of a named scene with plain goto tasks: every robot moves to a sampled collision-free

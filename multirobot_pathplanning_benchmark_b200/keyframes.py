@@ -27,25 +27,38 @@ def _robot_slice(scene: Scene, robot: str) -> slice:
 
 def solve_ik(scene: Scene, q_full: np.ndarray, robot: str, residual: Callable[[dict], np.ndarray],
              accept: Optional[Callable[[np.ndarray], bool]] = None, rng: Optional[np.random.RandomState] = None,
-             restarts: int = 60, tol: float = 1e-4, regularise: float = 1e-3) -> Optional[np.ndarray]:
+             restarts: int = 60, tol: float = 1e-4, regularise: float = 1e-3,
+             soft: Optional[Callable[[dict], np.ndarray]] = None) -> Optional[np.ndarray]:
     """Joint values of `robot` (others stay as in q_full) with |residual| < tol that `accept` (full q) agrees to.
-    `residual(X)` gets the frame poses {name: Tf} of the whole scene.  First start = current values, then
-    uniform restarts in the joint limits.  Returns the full configuration or None."""
+    `residual(X)` gets the frame poses {name: Tf} of the whole scene; `soft(X)` is minimised along with it but not
+    required to vanish (KOMO's sum-of-squares objectives).  First start = current values, then uniform restarts in
+    the joint limits.  Returns the full configuration or None."""
     rng = rng or np.random.RandomState(0)
     sl = _robot_slice(scene, robot)
     lim = scene.limits()[:, sl]
     q = np.array(q_full, np.float64)
     seed = q[sl].copy()
 
+    anchor = seed.copy()  # the regulariser picks the solution nearest to the start point of the attempt
+
     def fun(x):
         q[sl] = x
-        r = residual(scene.fk(q))
-        return np.concatenate([r, regularise * (x - seed)])
+        X = scene.fk(q)
+        r = [residual(X), regularise * (x - anchor)]
+        if soft is not None:
+            r.append(soft(X))
+        return np.concatenate(r)
 
+    n_hard = len(residual(scene.fk(q)))
     for t in range(restarts):
         x0 = np.clip(seed, lim[0], lim[1]) if t == 0 else rng.uniform(lim[0], lim[1])
+        anchor[:] = x0
         try:
-            sol = least_squares(fun, x0, bounds=(lim[0], lim[1]), xtol=1e-12, ftol=1e-12, gtol=1e-12, max_nfev=200)
+            sol = least_squares(fun, x0, bounds=(lim[0], lim[1]), xtol=1e-10, ftol=1e-10, gtol=1e-10, max_nfev=400)
+            # the regulariser (and soft terms) choose among the solutions; a second pass on the task residual
+            # alone, started there, removes the bias they leave on it
+            sol = least_squares(lambda x: fun(x)[:n_hard], sol.x, bounds=(lim[0], lim[1]), xtol=1e-12, ftol=1e-12, gtol=1e-12,
+                                max_nfev=100)
         except ValueError:
             continue
         q[sl] = sol.x

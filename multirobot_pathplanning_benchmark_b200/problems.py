@@ -40,7 +40,7 @@ def pick_place_sequence(scene: Scene, moves: Sequence[Move], free: Callable[[np.
     (list of (parent, child, q_at_attach)); asked of the same device that will answer the planner.
     tool: "vacuum" (UR10 + vacuum cup: tool point `<robot>ur_vacuum`, cup axis = local x, pointing down) or
     "two_finger" (UR10 + Robotiq: tool point `<robot>ur_gripper_center`, approach axis = local z pointing down,
-    jaws close along local y, aligned with a box side)."""
+    jaws close along local y, aligned with a box side) or "mobile" (mobile manipulator: tool point `<robot>gripper`)."""
     rng = np.random.RandomState(seed)
     # keyframes are solved with every other robot at home, like the reference's KOMO problems, which select the
     # acting robot's joints only (rai_config.py:3086-3090): the planner moves the others out of the way
@@ -50,18 +50,27 @@ def pick_place_sequence(scene: Scene, moves: Sequence[Move], free: Callable[[np.
     tasks: List[TaskSpec] = []
     sl = scene.robot_slices()
     for (robot, obj, goal_rel) in moves:
-        ee = robot + ("ur_vacuum" if tool == "vacuum" else "ur_gripper_center")
+        ee = robot + {"vacuum": "ur_vacuum", "two_finger": "ur_gripper_center", "mobile": "gripper"}[tool]
         X = cur.fk(q)
         box = X[obj]
         half_h = float(cur.frames[obj].shape.size[2]) / 2
-        if tool == "vacuum":
+        soft, extra_ok = None, (lambda qq: True)
+        if tool == "mobile":
+            # the gripper sphere (r = 30 mm) 2 mm above the top face; "arm pointing straight down" (gripper z = world z)
+            # is a soft objective as in the reference (rai_config.py:7786-7806: distance 0, positionDiff 0,
+            # scalarProductZZ 1 as sum-of-squares terms): the joint limits do not always allow it exactly
+            target = box.t + np.array([0, 0, half_h + 0.032])
+            res = lambda X, ee=ee, target=target: X[ee].t - target
+            soft = lambda X, ee=ee: 0.05 * (X[ee].R[:, 2] - np.array([0.0, 0.0, 1.0]))
+            extra_ok = lambda qq, ee=ee: cur.fk(qq)[ee].R[2, 2] > 0.8     # approach from above
+        elif tool == "vacuum":
             # cup 15 mm above the top face (the tool body, a capsule-modelled cylinder, ends 11 mm beyond the cup point)
             res = pick_residual(ee, box.t + np.array([0, 0, half_h + 0.015]), [1, 0, 0], [0, 0, -1])
         else:
             # grasp centre at the box centre, approach from above, jaws across the box's local x axis
             # (10 mm above it: the palm capsule ends 20 mm above the grasp centre, the box top is 25 mm above its centre)
             res = pick_residual(ee, box.t + np.array([0, 0, 0.01]), [0, 0, 1], [0, 0, -1], align=([0, 1, 0], box.R[:, 0]))
-        q_pick = solve_ik(cur, q, robot, res, accept=lambda qq: free(qq, relinks), rng=rng)
+        q_pick = solve_ik(cur, q, robot, res, accept=lambda qq: extra_ok(qq) and free(qq, relinks), rng=rng, soft=soft)
         if q_pick is None:
             raise RuntimeError(f"no collision-free pick keyframe for {robot} / {obj}")
         tasks.append(TaskSpec(f"{robot}pick_{obj}", [robot], q_pick[sl[robot][0]:sl[robot][1]].copy(), "pick", (ee, obj)))
@@ -117,13 +126,29 @@ def model_free_fn(model) -> Callable[[np.ndarray, list], bool]:
     return free
 
 
+def mobile_wall_moves(n_moves: int = 8, num_robots: int = 4) -> List[Move]:
+    """four mobile manipulators (rai_config.py:7690-7889): robot i carries the two boxes of column i of the wall at
+    y = -1 (top one first) to the goal wall at y = +1, where the column is rebuilt upside down (obj_1i -> bottom,
+    obj_0i -> top), goal heights as rai_config.py:7755-7761."""
+    size = np.array([0.5, 0.25, 0.15])
+    w = num_robots
+    plan = []
+    for i in range(num_robots):
+        for j in (1, 0):
+            x = i * size[0] * 1.075 - w / 2 * size[0] + size[0] / 2
+            plan.append((f"a{i}_", f"obj_{j}{i}", [x, 1.0, (1 - j) * size[2] * 1.01 + 0.05 + 0.1]))
+    return plan[:n_moves]
+
+
 PROBLEMS = {
     # scene name -> (moves, tool)
     "box_rearrangement": (box_rearrangement_moves, "vacuum"),
     "box_stacking": (box_stacking_moves, "two_finger"),
+    "mobile_wall_four": (mobile_wall_moves, "mobile"),
 }
 
 
 def manipulation_tasks(scene_name: str, model, n_moves: int = 4, seed: int = 0) -> List[TaskSpec]:
     moves, tool = PROBLEMS[scene_name]
-    return pick_place_sequence(model.base, moves(n_moves), model_free_fn(model), tool, seed=seed)
+    moves_list = moves(n_moves) if scene_name != "mobile_wall_four" else moves(n_moves, len(model.base.robots))
+    return pick_place_sequence(model.base, moves_list, model_free_fn(model), tool, seed=seed)
