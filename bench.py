@@ -470,9 +470,10 @@ def main():
         ttfs.run("2d_handover", "b200", 99, 200, 30, 30)   # warm-up
         tt = {}
         # 2d_handover: pick / handover / place sequence (6 modes); box_rearrangement: 2 pick-and-place moves with the
-        # vacuum tools (5 modes); box_stacking: the four arms stack 4 boxes (9 modes); keyframes from problems.py
+        # vacuum tools (5 modes); box_stacking: the four arms stack 4 boxes (9 modes); mobile_wall_four: two robots
+        # move their wall columns (4 moves, 9 modes); keyframes from problems.py
         for sname, n0, t0, cpu_seeds, n_moves in (("2d_handover", 500, 60, 3, 0), ("box_rearrangement", 2000, 200, 1, 2),
-                                                  ("box_stacking", 3000, 300, 1, 4)):
+                                                  ("box_stacking", 3000, 300, 1, 4), ("mobile_wall_four", 1500, 150, 1, 4)):
             gpu_runs = [ttfs.run(sname, "b200", seed, n0, t0, 120, n_moves=n_moves) for seed in range(3)]
             entry = {"samples_per_mode": n0, "pick_place_moves": n_moves, "modes": 6 if sname == "2d_handover" else 2 * n_moves + 1,
                      "b200_median_s": float(np.median([r["time_s"] for r in gpu_runs])), "b200_runs": gpu_runs}

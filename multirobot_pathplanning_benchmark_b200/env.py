@@ -167,6 +167,8 @@ class SceneModel:
         self.max_modes = max_modes
         self._device = device
         self._slots: Dict[tuple, int] = {}
+        self._by_signature: Dict[tuple, int] = {}
+        self._chains: Dict[tuple, Scene] = {}
         self._compiled: Dict[int, CompiledScene] = {}
         self._scenes: Dict[int, Scene] = {}
 
@@ -176,21 +178,51 @@ class SceneModel:
             self._device = CudaDevice(self.max_modes)  # raises without libmrb200.so / a GPU: no CPU fallback
         return self._device
 
+    @staticmethod
+    def _chain_key(relinks) -> tuple:
+        return tuple((p, c, np.asarray(q, np.float64).tobytes()) for p, c, q in relinks)
+
     def relinked(self, relinks: Sequence[Tuple[str, str, np.ndarray]]) -> Scene:
-        sc = self.base.copy()
-        for parent, child, q in relinks:
+        """base scene + the chain of re-parentings; chains are built from their longest known prefix (a mode's chain
+        extends its predecessor's by one link), so a new mode costs one frame-table copy and one attach"""
+        relinks = list(relinks)
+        k = len(relinks)
+        while k > 0 and self._chain_key(relinks[:k]) not in self._chains:
+            k -= 1
+        sc = self._chains[self._chain_key(relinks[:k])] if k else self.base
+        for i in range(k, len(relinks)):
+            parent, child, q = relinks[i]
+            sc = sc.copy()
             sc.attach(parent, child, np.asarray(q, np.float64))
+            self._chains[self._chain_key(relinks[:i + 1])] = sc
         return sc
+
+    @staticmethod
+    def _signature(sc: Scene, base: Scene) -> tuple:
+        """what a chain of re-parentings changed: (object, parent, rounded relative pose, contact) of every frame that
+        differs from the base scene.  Two chains with the same signature are the same kinematic tree (the pose of a
+        held object depends on the holder's joints only, not on where the other robots stood)."""
+        out = []
+        for n, f in sc.frames.items():
+            b = base.frames[n]
+            if f.parent != b.parent or f.rel is not b.rel:
+                out.append((n, f.parent, np.round(np.concatenate([f.rel.t, f.rel.R.ravel()]), 7).tobytes(), f.contact))
+        return tuple(sorted(out))
 
     def slot_for(self, key: tuple, relinks: Sequence[Tuple[str, str, np.ndarray]] = ()) -> int:
         if key not in self._slots:
-            if len(self._slots) >= self.max_modes:
-                raise RuntimeError(f"more than {self.max_modes} distinct kinematic trees; raise max_modes")
-            slot = len(self._slots)
             sc = self.relinked(relinks)
+            sig = self._signature(sc, self.base)
+            if sig in self._by_signature:         # an equivalent tree is already on the device
+                self._slots[key] = self._by_signature[sig]
+                return self._slots[key]
+            if len(self._compiled) >= self.max_modes:
+                raise RuntimeError(f"more than {self.max_modes} distinct kinematic trees; raise max_modes")
+            slot = len(self._compiled)
             cs = compile_blob(sc, self.tol)
             self.device.set_mode(slot, cs)
             self._slots[key] = slot
+            self._by_signature[sig] = slot
             self._compiled[slot] = cs
             self._scenes[slot] = sc
         return self._slots[key]

@@ -209,7 +209,12 @@ class Scene:
         return f
 
     def copy(self) -> "Scene":
-        return copy.deepcopy(self)
+        """Independent frame table; transforms, limits and shapes are shared (they are never mutated in place:
+        attach / remove replace the `rel` object and rebuild the table)."""
+        sc = Scene()
+        sc.frames = {n: copy.copy(f) for n, f in self.frames.items()}
+        sc.robots = list(self.robots)
+        return sc
 
     # ---- joint vector layout ----------------------------------------------------
     def dof_frames(self) -> List[Frame]:
@@ -346,8 +351,33 @@ class Scene:
         return [f.name for f in self.frames.values() if f.shape is not None and f.contact != 0]
 
     def collidable_pairs(self) -> List[Tuple[str, str]]:
+        """all (a, b) with can_collide(a, b), a before b in frame order (same rule, link tables computed once)"""
         names = self.collision_shapes()
-        return [(a, b) for i, a in enumerate(names) for b in names[i + 1:] if self.can_collide(a, b)]
+        link = {n: self.link_of(n) for n in names}
+        up: Dict[str, Optional[str]] = {}
+
+        def parent_link(l):
+            if l not in up:
+                up[l] = self.parent_link(l)
+            return up[l]
+
+        anc = {}   # shape -> the ancestor links its negative contact flag suppresses
+        for n in names:
+            k, p, out = -self.frames[n].contact, link[n], set()
+            for _ in range(max(k, 0)):
+                p = parent_link(p)
+                if p is None:
+                    break
+                out.add(p)
+            anc[n] = out
+        pairs = []
+        for i, a in enumerate(names):
+            la, sa = link[a], anc[a]
+            for b in names[i + 1:]:
+                lb = link[b]
+                if la != lb and lb not in sa and la not in anc[b]:
+                    pairs.append((a, b))
+        return pairs
 
     def is_moving(self, name: str) -> bool:
         f = self.frames[name]
