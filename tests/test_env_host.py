@@ -257,3 +257,23 @@ def test_reference_shortcutter_on_batched_path_checks(reference, envmod):
     assert ca < results[True][1] + 1e-12
     print("device calls during shortcutting, batched / per-query:", calls_b, calls_r)
     assert calls_b["edges"] * 3 < calls_r["edges"]
+
+
+@pytest.mark.parametrize("planner", ["eitstar", "aitstar"])
+def test_reference_informed_tree_planners_solve_b200_handover(reference, envmod, planner):
+    """EIT* / AIT* with their default configuration: mode validation through is_collision_free_for_robot
+    (P/planners/mode_validation.py:101), sparse-then-dense edge checks through N_start / N_max / N
+    (P/planners/planner_eitstar.py), radius neighbours from batch_config_dist."""
+    from multi_robot_multi_goal_planning.planners.itstar_base import BaseITConfig
+    from multi_robot_multi_goal_planning.planners.planner_aitstar import AITstar
+    from multi_robot_multi_goal_planning.planners.planner_eitstar import EITstar
+    from multi_robot_multi_goal_planning.planners.termination_conditions import RuntimeTerminationCondition
+    dev = OracleSceneDevice()
+    env = envmod.b200_two_dim_handover(device=dev)
+    np.random.seed(2)
+    random.seed(2)
+    cls = EITstar if planner == "eitstar" else AITstar
+    path, _ = cls(env, BaseITConfig()).plan(RuntimeTerminationCondition(240), optimize=False)
+    assert path is not None and env.is_valid_plan(path) and env.is_terminal_mode(path[-1].mode)
+    assert len({tuple(s.mode.task_ids) for s in path}) == 6
+    assert dev.calls["robot"] > 0 and dev.calls["edges"] > 0
