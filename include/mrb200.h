@@ -89,6 +89,19 @@ int mrb200_check_edges(const mrb200_scene_t* scene, int slot, const float* q1_de
                        int64_t E, double resolution, const int32_t* N_dev, int32_t n_start, int32_t n_max,
                        int include_endpoints, float tol, uint8_t* free_dev, int32_t* first_pos_dev,
                        mrb200_stream_t stream);
+/* The planners' one-query-at-a-time seam with HOST buffers (is_collision_free / is_collision_free_for_robot /
+ * is_edge_collision_free called per configuration or edge, e.g. P/planners/collision_free_sampler.py:106-143,
+ * P/planners/rrtstar_base.py:626-629): copy in, launch, copy out and synchronise inside one call, through
+ * staging buffers owned by the scene handle (grown on demand; calls on one handle are serialised).  Host
+ * pointers may be pageable.  relevant_host / other_host: null for the plain rule, else as in
+ * mrb200_check_configs_for_robot.  N_host: null = from the resolution.  first_pos_host nullable. */
+int mrb200_query_configs_host(mrb200_scene_t* scene, int slot, const float* q_host /*[B, D]*/, int64_t B, float tol,
+                              const uint8_t* relevant_host, const uint8_t* other_host, int n_shapes,
+                              uint8_t* free_host, mrb200_stream_t stream);
+int mrb200_query_edges_host(mrb200_scene_t* scene, int slot, const float* q1_host, const float* q2_host, int64_t E,
+                            double resolution, const int32_t* N_host, int32_t n_start, int32_t n_max,
+                            int include_endpoints, float tol, uint8_t* free_host, int32_t* first_pos_host,
+                            mrb200_stream_t stream);
 /* introspection of a slot: D, n_shapes, n_pairs (dynamic), shared memory bytes per CTA */
 int mrb200_scene_info(const mrb200_scene_t* scene, int slot, int32_t* out4);
 

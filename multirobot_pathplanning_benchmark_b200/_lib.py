@@ -34,6 +34,9 @@ SIGNATURES = {
                                                  c_vp, c_vp]),
     "mrb200_check_edges": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int32,
                                      C.c_int, C.c_float, c_vp, c_vp, c_vp]),
+    "mrb200_query_configs_host": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_float, c_vp, c_vp, C.c_int, c_vp, c_vp]),
+    "mrb200_query_edges_host": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int32, C.c_int,
+                                          C.c_float, c_vp, c_vp, c_vp]),
     "mrb200_scene_info": (C.c_int, [c_vp, C.c_int, c_i32p]),
     "mrb200_batch_dist": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, c_vp, c_vp]),
     "mrb200_batch_cost": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, C.c_double, c_vp,

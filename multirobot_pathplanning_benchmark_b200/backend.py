@@ -11,6 +11,7 @@ is_collision_free_for_robot (rai_base_env.py:515-615), is_edge_collision_free
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Optional, Sequence, Tuple
 
@@ -41,6 +42,8 @@ class AbstractBackend:
                  rects_minmax: Sequence[Tuple[Sequence[float], Sequence[float]]] = (), device=None):
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.n_agents, self.dim = n_agents, dim
         self.D = n_agents * dim
         radii = np.ascontiguousarray(radii, np.float64)
@@ -99,6 +102,8 @@ class SceneBackend:
     def __init__(self, max_modes: int = 64, device=None):
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mrb200_scene_create(int(max_modes), C.byref(h)), "scene_create")
@@ -181,6 +186,53 @@ class SceneBackend:
                 int(include_endpoints), -1.0 if tol is None else float(tol), free.data_ptr(), first.data_ptr(),
                 _stream(q1.device)), "check_edges")
         return free.view(torch.bool), first
+
+
+    # ---- the planners' one-query-at-a-time seam: numpy in, numpy out, one library call (copies + launch + sync) ----
+    def query_configs_host(self, slot: int, q: np.ndarray, tol: Optional[float] = None, relevant: Optional[np.ndarray] = None,
+                           other: Optional[np.ndarray] = None) -> np.ndarray:
+        q = np.ascontiguousarray(q, np.float32)
+        if q.ndim != 2 or q.shape[1] != self.compiled[slot].dof:
+            raise ValueError(f"q must be [B, {self.compiled[slot].dof}]")
+        out = np.empty(q.shape[0], np.uint8)
+        rel = oth = None
+        n = 0
+        if relevant is not None:
+            rel, oth = np.ascontiguousarray(relevant, np.uint8), np.ascontiguousarray(other, np.uint8)
+            n = len(rel)
+        with self._on_device():
+            rc = self.lib.mrb200_query_configs_host(
+                self.handle, slot, q.ctypes.data, q.shape[0], -1.0 if tol is None else float(tol),
+                rel.ctypes.data if rel is not None else None, oth.ctypes.data if oth is not None else None, n,
+                out.ctypes.data, _stream(self.device))
+        if rc:
+            _lib.check(rc, "query_configs_host")
+        return out
+
+    def query_edges_host(self, slot: int, q1: np.ndarray, q2: np.ndarray, resolution: float, N: Optional[np.ndarray] = None,
+                         n_start: int = 0, n_max: Optional[int] = None, include_endpoints: bool = False,
+                         tol: Optional[float] = None):
+        q1, q2 = np.ascontiguousarray(q1, np.float32), np.ascontiguousarray(q2, np.float32)
+        if q1.shape != q2.shape or q1.ndim != 2 or q1.shape[1] != self.compiled[slot].dof:
+            raise ValueError(f"q1, q2 must both be [E, {self.compiled[slot].dof}]")
+        E = q1.shape[0]
+        Nh = None if N is None else np.ascontiguousarray(N, np.int32)
+        free, first = np.empty(E, np.uint8), np.empty(E, np.int32)
+        with self._on_device():
+            rc = self.lib.mrb200_query_edges_host(
+                self.handle, slot, q1.ctypes.data, q2.ctypes.data, E, float(resolution), Nh.ctypes.data if Nh is not None else None,
+                int(n_start), -1 if n_max is None else int(n_max), int(include_endpoints), -1.0 if tol is None else float(tol),
+                free.ctypes.data, first.ctypes.data, _stream(self.device))
+        if rc:
+            _lib.check(rc, "query_edges_host")
+        return free, first
+
+    def _on_device(self):
+        """device guard that costs nothing when this backend's GPU already is the current one (the latency-critical
+        single-query path)"""
+        if torch.cuda.current_device() == self.device.index:
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
 
 
 def check_configs_host(be: SceneBackend, slot: int, q_host: torch.Tensor, out_host: torch.Tensor,

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/mrb200.h"
@@ -41,6 +42,12 @@ struct ModeSlot {
 struct mrb200_scene {
     std::vector<ModeSlot> slots;
     int* counter = nullptr;  // device scratch for the edge scheduler
+    // staging of the host-buffer query entry points (mrb200_query_*_host): one device and one pinned host
+    // buffer, grown on demand, guarded by `mu`
+    std::mutex mu;
+    unsigned char* stage_dev = nullptr;
+    unsigned char* stage_pin = nullptr;
+    size_t stage_bytes = 0;
 };
 
 struct mrb200_abstract {
@@ -148,6 +155,8 @@ int mrb200_scene_destroy(mrb200_scene_t* sc) {
     if (!sc) return MRB200_OK;
     for (auto& s : sc->slots) cudaFree(s.blob);
     cudaFree(sc->counter);
+    cudaFree(sc->stage_dev);
+    cudaFreeHost(sc->stage_pin);
     delete sc;
     return MRB200_OK;
 }
@@ -280,6 +289,85 @@ int mrb200_check_edges(const mrb200_scene_t* sc, int slot, const float* q1, cons
     cudaError_t e = mrb::launch_check_edges(p, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "check_edges");
     g_launches++;
+    return MRB200_OK;
+}
+
+// host-buffer queries: stage -> H2D -> kernel -> D2H -> synchronise, all inside the call
+static int stage_reserve(mrb200_scene_t* sc, size_t bytes, cudaStream_t st) {
+    if (bytes <= sc->stage_bytes) return MRB200_OK;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "query: sync");
+    cudaFree(sc->stage_dev);
+    cudaFreeHost(sc->stage_pin);
+    sc->stage_dev = sc->stage_pin = nullptr;
+    sc->stage_bytes = 0;
+    size_t cap = 4096;
+    while (cap < bytes) cap *= 2;
+    e = cudaMalloc(&sc->stage_dev, cap);
+    if (e != cudaSuccess) return cuda_fail(e, "query: cudaMalloc");
+    e = cudaMallocHost(&sc->stage_pin, cap);
+    if (e != cudaSuccess) return cuda_fail(e, "query: cudaMallocHost");
+    sc->stage_bytes = cap;
+    return MRB200_OK;
+}
+
+static size_t up16(size_t x) { return (x + 15) & ~size_t(15); }
+
+int mrb200_query_configs_host(mrb200_scene_t* sc, int slot, const float* q_host, int64_t B, float tol,
+                              const uint8_t* relevant_host, const uint8_t* other_host, int n_shapes, uint8_t* free_host,
+                              mrb200_stream_t stream) {
+    const ModeSlot* s = get_slot(sc, slot);
+    if (!s) return fail(MRB200_ERR_ARG, "query_configs_host: empty mode slot %d", slot);
+    if (B < 0 || (B && (!q_host || !free_host)) || ((relevant_host != nullptr) != (other_host != nullptr)))
+        return fail(MRB200_ERR_ARG, "query_configs_host: bad argument");
+    if (B == 0) return MRB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lock(sc->mu);
+    const size_t qb = up16((size_t)B * s->D * 4), fb = up16((size_t)B);
+    int rc = stage_reserve(sc, qb + fb, st);
+    if (rc) return rc;
+    memcpy(sc->stage_pin, q_host, (size_t)B * s->D * 4);
+    cudaError_t e = cudaMemcpyAsync(sc->stage_dev, sc->stage_pin, (size_t)B * s->D * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "query_configs_host: H2D");
+    const float* qd = (const float*)sc->stage_dev;
+    uint8_t* fd = sc->stage_dev + qb;
+    rc = relevant_host ? mrb200_check_configs_for_robot(sc, slot, qd, B, tol, relevant_host, other_host, n_shapes, fd, stream)
+                       : mrb200_check_configs(sc, slot, qd, B, tol, fd, nullptr, 0, stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(sc->stage_pin + qb, fd, (size_t)B, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "query_configs_host: D2H");
+    memcpy(free_host, sc->stage_pin + qb, (size_t)B);
+    return MRB200_OK;
+}
+
+int mrb200_query_edges_host(mrb200_scene_t* sc, int slot, const float* q1_host, const float* q2_host, int64_t E,
+                            double resolution, const int32_t* N_host, int32_t n_start, int32_t n_max, int include_endpoints,
+                            float tol, uint8_t* free_host, int32_t* first_pos_host, mrb200_stream_t stream) {
+    const ModeSlot* s = get_slot(sc, slot);
+    if (!s) return fail(MRB200_ERR_ARG, "query_edges_host: empty mode slot %d", slot);
+    if (E < 0 || (E && (!q1_host || !q2_host || !free_host))) return fail(MRB200_ERR_ARG, "query_edges_host: bad argument");
+    if (E == 0) return MRB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lock(sc->mu);
+    const size_t qb = up16((size_t)E * s->D * 4), nb = up16((size_t)E * 4), fb = up16((size_t)E);
+    // layout: q1 | q2 | N | first | free   (the inputs are one contiguous H2D copy, the outputs one D2H copy)
+    int rc = stage_reserve(sc, 2 * qb + 2 * nb + fb, st);
+    if (rc) return rc;
+    memcpy(sc->stage_pin, q1_host, (size_t)E * s->D * 4);
+    memcpy(sc->stage_pin + qb, q2_host, (size_t)E * s->D * 4);
+    if (N_host) memcpy(sc->stage_pin + 2 * qb, N_host, (size_t)E * 4);
+    cudaError_t e = cudaMemcpyAsync(sc->stage_dev, sc->stage_pin, 2 * qb + (N_host ? nb : 0), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "query_edges_host: H2D");
+    unsigned char* d = sc->stage_dev;
+    rc = mrb200_check_edges(sc, slot, (const float*)d, (const float*)(d + qb), E, resolution, N_host ? (const int32_t*)(d + 2 * qb) : nullptr,
+                            n_start, n_max, include_endpoints, tol, d + 2 * qb + 2 * nb, (int32_t*)(d + 2 * qb + nb), stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(sc->stage_pin + 2 * qb + nb, d + 2 * qb + nb, nb + fb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "query_edges_host: D2H");
+    if (first_pos_host) memcpy(first_pos_host, sc->stage_pin + 2 * qb + nb, (size_t)E * 4);
+    memcpy(free_host, sc->stage_pin + 2 * qb + 2 * nb, (size_t)E);
     return MRB200_OK;
 }
 

@@ -75,6 +75,14 @@ class CudaDevice:
         return self.be.check_edges(slot, self._t(q1), self._t(q2), resolution, N=N, n_start=n_start, n_max=n_max,
                                    include_endpoints=include_endpoints, tol=tol)
 
+    # single-query seam (numpy in, numpy out): one library call does the copies, the launch and the synchronisation
+    def query_configs(self, slot, q, tol=None, rel=None, oth=None):
+        return self.be.query_configs_host(slot, q, tol, rel, oth)
+
+    def query_edges(self, slot, q1, q2, resolution, N=None, n_start=0, n_max=None, include_endpoints=False, tol=None):
+        return self.be.query_edges_host(slot, q1, q2, resolution, N=N, n_start=n_start, n_max=n_max,
+                                        include_endpoints=include_endpoints, tol=tol)
+
     @staticmethod
     def to_numpy(x):
         return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
@@ -371,14 +379,28 @@ if HAVE_REFERENCE:
                     self.model.device.check_configs(slot, b.astype(np.float32))))
                 if hit is not None:
                     return hit
-            out = self.model.device.check_configs(self._slot, np.asarray(q.state(), np.float32)[None], collision_tolerance)
+            return self._one_config(np.asarray(q.state(), np.float32)[None], collision_tolerance)
+
+        def _one_config(self, q, tol=None, rel=None, oth=None) -> bool:
+            """one configuration through the device's host-buffer entry (mrb200_query_configs_host) when it has one"""
+            dev = self.model.device
+            fast = getattr(dev, "query_configs", None)
+            if fast is not None:
+                return bool(fast(self._slot, q, tol, rel, oth)[0])
+            out = dev.check_configs(self._slot, q, tol) if rel is None else dev.check_configs_for_robot(self._slot, q, rel, oth, tol)
             return bool(CudaDevice.to_numpy(out)[0])
+
+        def _edges(self, a, b, resolution, **kw):
+            """(free, first colliding position) of edges as numpy arrays, through mrb200_query_edges_host when available"""
+            dev = self.model.device
+            fast = getattr(dev, "query_edges", None)
+            free, first = (fast or dev.check_edges)(self._slot, a, b, resolution, **kw)
+            return CudaDevice.to_numpy(free), CudaDevice.to_numpy(first)
 
         def is_collision_free_np(self, q, m, collision_tolerance=None, set_mode: bool = True) -> bool:
             if set_mode:
                 self.set_to_mode(m)
-            out = self.model.device.check_configs(self._slot, np.asarray(q, np.float32)[None], collision_tolerance)
-            return bool(CudaDevice.to_numpy(out)[0])
+            return self._one_config(np.asarray(q, np.float32)[None], collision_tolerance)
 
         def _robot_masks(self, robots: List[str], m: "Mode"):
             cs = self.model.compiled(self._slot)
@@ -400,8 +422,7 @@ if HAVE_REFERENCE:
             if set_mode:
                 self.set_to_mode(m)
             rel, oth = self._robot_masks(list(r), m)
-            out = self.model.device.check_configs_for_robot(self._slot, np.asarray(q, np.float32)[None], rel, oth, collision_tolerance)
-            return bool(CudaDevice.to_numpy(out)[0])
+            return self._one_config(np.asarray(q, np.float32)[None], collision_tolerance, rel, oth)
 
         def is_edge_collision_free(self, q1, q2, m, resolution=None, tolerance=None, include_endpoints: bool = False,
                                    N_start: int = 0, N_max: Optional[int] = None, N: Optional[int] = None) -> bool:
@@ -420,14 +441,13 @@ if HAVE_REFERENCE:
                 slot = self._slot
                 key = (slot, q1.state().tobytes(), q2.state().tobytes(), int(N), float(resolution), bool(include_endpoints),
                        None if tolerance is None else float(tolerance))
-                hit = self.spec_cache.edge_window(key, N_start, N_max, int(N), lambda: CudaDevice.to_numpy(
-                    self.model.device.check_edges(slot, a, b, resolution, N=Ns, include_endpoints=include_endpoints,
-                                                  tol=tolerance)[1])[0])
+                hit = self.spec_cache.edge_window(key, N_start, N_max, int(N), lambda: self._edges(
+                    a, b, resolution, N=Ns, include_endpoints=include_endpoints, tol=tolerance)[1][0])
                 if hit is not None:
                     return hit
-            free, _ = self.model.device.check_edges(self._slot, a, b, resolution, N=Ns, n_start=N_start, n_max=N_max,
-                                                    include_endpoints=include_endpoints, tol=tolerance)
-            return bool(CudaDevice.to_numpy(free)[0])
+            free, _ = self._edges(a, b, resolution, N=Ns, n_start=N_start, n_max=N_max, include_endpoints=include_endpoints,
+                                  tol=tolerance)
+            return bool(free[0])
 
         def is_path_collision_free(self, path, binary_order: bool = True, resolution=None, tolerance=None,
                                    check_edges_in_order: bool = False, check_start_and_end: bool = True) -> bool:

@@ -164,3 +164,33 @@ def test_held_object_modes(cuda_lib, name, parent, child):
     assert np.max(np.abs(pen.cpu().numpy() - open_)) < 2e-5
     base_free = model.check_configs(base_slot, torch.from_numpy(q).cuda()).cpu().numpy()
     assert (free.cpu().numpy() != base_free).any()  # the mode really changes the answer
+
+
+def test_host_buffer_queries_equal_device_buffer_calls(be):
+    """mrb200_query_configs_host / mrb200_query_edges_host (the planners' single-query seam): same answers as the
+    device-buffer entry points, for one query and for small batches, plain rule and per-robot rule, edge windows"""
+    slot, sc, cs, kw = be.scenes["box_rearrangement"]
+    q = uniform_configs(sc, 777, 31)
+    want = be.check_configs(slot, torch.from_numpy(q).cuda()).cpu().numpy()
+    assert np.array_equal(be.query_configs_host(slot, q), want)
+    for i in (0, 1, 500):
+        assert be.query_configs_host(slot, q[i:i + 1])[0] == want[i]
+    assert np.array_equal(be.query_configs_host(slot, q, tol=0.0),
+                          be.check_configs(slot, torch.from_numpy(q).cuda(), tol=0.0).cpu().numpy())
+    rel = np.array(["a1_" in n for n in cs.shape_names], np.uint8)
+    oth = np.array(["a2_" in n for n in cs.shape_names], np.uint8)
+    assert np.array_equal(be.query_configs_host(slot, q, relevant=rel, other=oth),
+                          be.check_configs_for_robot(slot, torch.from_numpy(q).cuda(), rel, oth).cpu().numpy())
+    q2 = q + np.random.default_rng(2).uniform(-0.3, 0.3, q.shape).astype(np.float32)
+    t1, t2 = torch.from_numpy(q).cuda(), torch.from_numpy(q2).cuda()
+    for kwargs in ({}, {"n_start": 2, "n_max": 9}, {"include_endpoints": True}):
+        f, p = be.check_edges(slot, t1, t2, 0.01, **kwargs)
+        fh, ph = be.query_edges_host(slot, q, q2, 0.01, **kwargs)
+        assert np.array_equal(fh, f.cpu().numpy()) and np.array_equal(ph, p.cpu().numpy())
+    N = np.full(len(q), 17, np.int32)
+    f, p = be.check_edges(slot, t1, t2, 0.01, N=torch.from_numpy(N).cuda())
+    fh, ph = be.query_edges_host(slot, q, q2, 0.01, N=N)
+    assert np.array_equal(fh, f.cpu().numpy()) and np.array_equal(ph, p.cpu().numpy())
+    assert be.query_configs_host(slot, q[:0]).shape == (0,)
+    with pytest.raises(Exception):
+        be.query_configs_host(slot, q[:, :5])
