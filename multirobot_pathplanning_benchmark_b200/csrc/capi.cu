@@ -46,7 +46,8 @@ struct mrb200_scene {
     // buffer, grown on demand, guarded by `mu`
     std::mutex mu;
     unsigned char* stage_dev = nullptr;
-    unsigned char* stage_pin = nullptr;
+    unsigned char* stage_pin = nullptr;      // pinned + mapped host memory
+    unsigned char* stage_pin_dev = nullptr;  // its device-side alias: tiny queries are read / written in place
     size_t stage_bytes = 0;
 };
 
@@ -212,8 +213,11 @@ int mrb200_scene_info(const mrb200_scene_t* sc, int slot, int32_t* out4) {
     return MRB200_OK;
 }
 
+constexpr int64_t MRB200_ZERO_COPY_MAX = 64;  // host-buffer queries up to this size run on mapped host memory in place
+
 static int check_configs_impl(const mrb200_scene_t* sc, int slot, const float* q, int64_t B, float tol, uint8_t* free_dev,
-                              float* pen_dev, int full_eval, const mrb::RobotRule& rule, mrb200_stream_t stream) {
+                              float* pen_dev, int full_eval, const mrb::RobotRule& rule, mrb200_stream_t stream,
+                              bool allow_bulk = true) {
     const ModeSlot* s = get_slot(sc, slot);
     if (!s) return fail(MRB200_ERR_ARG, "check_configs: empty mode slot %d", slot);
     if (B < 0 || (B && (!q || !free_dev))) return fail(MRB200_ERR_ARG, "check_configs: bad argument");
@@ -230,7 +234,7 @@ static int check_configs_impl(const mrb200_scene_t* sc, int slot, const float* q
     p.flags = free_dev;
     p.pen_out = pen_dev;
     p.full_eval = full_eval;
-    p.bulk_ok = (((uintptr_t)q) & 15) == 0 && ((s->D * 4 * 32) % 16 == 0);
+    p.bulk_ok = allow_bulk && (((uintptr_t)q) & 15) == 0 && ((s->D * 4 * 32) % 16 == 0);
     p.rule = rule;
     cudaError_t e = mrb::launch_check_configs(p, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "check_configs");
@@ -299,14 +303,16 @@ static int stage_reserve(mrb200_scene_t* sc, size_t bytes, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_fail(e, "query: sync");
     cudaFree(sc->stage_dev);
     cudaFreeHost(sc->stage_pin);
-    sc->stage_dev = sc->stage_pin = nullptr;
+    sc->stage_dev = sc->stage_pin = sc->stage_pin_dev = nullptr;
     sc->stage_bytes = 0;
     size_t cap = 4096;
     while (cap < bytes) cap *= 2;
     e = cudaMalloc(&sc->stage_dev, cap);
     if (e != cudaSuccess) return cuda_fail(e, "query: cudaMalloc");
-    e = cudaMallocHost(&sc->stage_pin, cap);
-    if (e != cudaSuccess) return cuda_fail(e, "query: cudaMallocHost");
+    e = cudaHostAlloc(&sc->stage_pin, cap, cudaHostAllocMapped);
+    if (e != cudaSuccess) return cuda_fail(e, "query: cudaHostAlloc");
+    e = cudaHostGetDevicePointer((void**)&sc->stage_pin_dev, sc->stage_pin, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "query: cudaHostGetDevicePointer");
     sc->stage_bytes = cap;
     return MRB200_OK;
 }
@@ -327,14 +333,27 @@ int mrb200_query_configs_host(mrb200_scene_t* sc, int slot, const float* q_host,
     int rc = stage_reserve(sc, qb + fb, st);
     if (rc) return rc;
     memcpy(sc->stage_pin, q_host, (size_t)B * s->D * 4);
-    cudaError_t e = cudaMemcpyAsync(sc->stage_dev, sc->stage_pin, (size_t)B * s->D * 4, cudaMemcpyHostToDevice, st);
+    // a handful of queries: the kernel reads the configurations from, and writes the flags to, the mapped host
+    // buffer directly -- two copy calls less per query; larger batches go through device staging
+    const bool in_place = B <= MRB200_ZERO_COPY_MAX;
+    cudaError_t e = cudaSuccess;
+    if (!in_place) e = cudaMemcpyAsync(sc->stage_dev, sc->stage_pin, (size_t)B * s->D * 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "query_configs_host: H2D");
-    const float* qd = (const float*)sc->stage_dev;
-    uint8_t* fd = sc->stage_dev + qb;
-    rc = relevant_host ? mrb200_check_configs_for_robot(sc, slot, qd, B, tol, relevant_host, other_host, n_shapes, fd, stream)
-                       : mrb200_check_configs(sc, slot, qd, B, tol, fd, nullptr, 0, stream);
+    unsigned char* base = in_place ? sc->stage_pin_dev : sc->stage_dev;
+    const float* qd = (const float*)base;
+    uint8_t* fd = base + qb;
+    mrb::RobotRule rule{};
+    if (relevant_host) {
+        if (n_shapes != s->n_shapes) return fail(MRB200_ERR_ARG, "query_configs_host: need %d shape flags", s->n_shapes);
+        rule.enabled = 1;
+        for (int i = 0; i < n_shapes; i++) {
+            if (relevant_host[i]) rule.rel[i >> 6] |= 1ull << (i & 63);
+            if (other_host[i]) rule.oth[i >> 6] |= 1ull << (i & 63);
+        }
+    }
+    rc = check_configs_impl(sc, slot, qd, B, tol, fd, nullptr, relevant_host ? 1 : 0, rule, stream, /*allow_bulk=*/!in_place);
     if (rc) return rc;
-    e = cudaMemcpyAsync(sc->stage_pin + qb, fd, (size_t)B, cudaMemcpyDeviceToHost, st);
+    if (!in_place) e = cudaMemcpyAsync(sc->stage_pin + qb, fd, (size_t)B, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "query_configs_host: D2H");
     memcpy(free_host, sc->stage_pin + qb, (size_t)B);
@@ -357,13 +376,15 @@ int mrb200_query_edges_host(mrb200_scene_t* sc, int slot, const float* q1_host, 
     memcpy(sc->stage_pin, q1_host, (size_t)E * s->D * 4);
     memcpy(sc->stage_pin + qb, q2_host, (size_t)E * s->D * 4);
     if (N_host) memcpy(sc->stage_pin + 2 * qb, N_host, (size_t)E * 4);
-    cudaError_t e = cudaMemcpyAsync(sc->stage_dev, sc->stage_pin, 2 * qb + (N_host ? nb : 0), cudaMemcpyHostToDevice, st);
+    const bool in_place = E <= MRB200_ZERO_COPY_MAX;
+    cudaError_t e = cudaSuccess;
+    if (!in_place) e = cudaMemcpyAsync(sc->stage_dev, sc->stage_pin, 2 * qb + (N_host ? nb : 0), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "query_edges_host: H2D");
-    unsigned char* d = sc->stage_dev;
+    unsigned char* d = in_place ? sc->stage_pin_dev : sc->stage_dev;
     rc = mrb200_check_edges(sc, slot, (const float*)d, (const float*)(d + qb), E, resolution, N_host ? (const int32_t*)(d + 2 * qb) : nullptr,
                             n_start, n_max, include_endpoints, tol, d + 2 * qb + 2 * nb, (int32_t*)(d + 2 * qb + nb), stream);
     if (rc) return rc;
-    e = cudaMemcpyAsync(sc->stage_pin + 2 * qb + nb, d + 2 * qb + nb, nb + fb, cudaMemcpyDeviceToHost, st);
+    if (!in_place) e = cudaMemcpyAsync(sc->stage_pin + 2 * qb + nb, d + 2 * qb + nb, nb + fb, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "query_edges_host: D2H");
     if (first_pos_host) memcpy(first_pos_host, sc->stage_pin + 2 * qb + nb, (size_t)E * 4);
