@@ -61,6 +61,15 @@ int mrb200_abstract_check_edges(const mrb200_abstract_t* env, const double* q1_d
                                 int32_t n_max, int include_endpoints, uint8_t* free_dev,
                                 int32_t* first_pos_dev, mrb200_stream_t stream);
 
+/* the same two queries with HOST buffers (one call = staging + launch + synchronisation; mapped pinned staging owned
+ * by the handle, calls serialised per handle): the planners' one-query-at-a-time seam, see mrb200_query_configs_host */
+int mrb200_abstract_query_configs_host(mrb200_abstract_t* env, const double* q_host, int64_t B, uint8_t* free_host,
+                                       mrb200_stream_t stream);
+int mrb200_abstract_query_edges_host(mrb200_abstract_t* env, const double* q1_host, const double* q2_host, int64_t E,
+                                     double resolution, const int32_t* N_host, int32_t n_start, int32_t n_max,
+                                     int include_endpoints, uint8_t* free_host, int32_t* first_pos_host,
+                                     mrb200_stream_t stream);
+
 /* ---- primitive scenes (rai-style): rai_env, P/problems/rai_base_env.py:442-836 ----
  * A scene holds `max_modes` slots; each slot is a compiled scene blob (layout:
  * multirobot_pathplanning_benchmark_b200/csrc/scene_blob.h) for one mode's kinematic tree

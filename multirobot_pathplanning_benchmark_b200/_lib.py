@@ -26,6 +26,9 @@ SIGNATURES = {
     "mrb200_abstract_check_configs": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
     "mrb200_abstract_check_edges": (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int32,
                                               C.c_int, c_vp, c_vp, c_vp]),
+    "mrb200_abstract_query_configs_host": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
+    "mrb200_abstract_query_edges_host": (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int32, C.c_int,
+                                                   c_vp, c_vp, c_vp]),
     "mrb200_scene_create": (C.c_int, [C.c_int, C.POINTER(c_vp)]),
     "mrb200_scene_destroy": (C.c_int, [c_vp]),
     "mrb200_scene_set_mode": (C.c_int, [c_vp, C.c_int, c_vp, C.c_size_t, c_vp]),

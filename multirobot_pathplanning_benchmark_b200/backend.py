@@ -96,6 +96,33 @@ class AbstractBackend:
         return free.view(torch.bool), first
 
 
+    # ---- single-query seam: numpy fp64 in, numpy out, one library call ----
+    def query_configs_host(self, q: np.ndarray) -> np.ndarray:
+        q = np.ascontiguousarray(q, np.float64)
+        if q.ndim != 2 or q.shape[1] != self.D:
+            raise ValueError(f"q must be [B, {self.D}]")
+        out = np.empty(q.shape[0], np.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrb200_abstract_query_configs_host(self.handle, q.ctypes.data, q.shape[0], out.ctypes.data,
+                                                                   _stream(self.device)), "abstract_query_configs_host")
+        return out.view(np.bool_)
+
+    def query_edges_host(self, q1: np.ndarray, q2: np.ndarray, resolution: float, N: Optional[np.ndarray] = None, n_start: int = 0,
+                         n_max: Optional[int] = None, include_endpoints: bool = False):
+        q1, q2 = np.ascontiguousarray(q1, np.float64), np.ascontiguousarray(q2, np.float64)
+        if q1.shape != q2.shape or q1.ndim != 2 or q1.shape[1] != self.D:
+            raise ValueError(f"q1, q2 must both be [E, {self.D}]")
+        E = q1.shape[0]
+        Nh = None if N is None else np.ascontiguousarray(N, np.int32)
+        free, first = np.empty(E, np.uint8), np.empty(E, np.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrb200_abstract_query_edges_host(
+                self.handle, q1.ctypes.data, q2.ctypes.data, E, float(resolution), Nh.ctypes.data if Nh is not None else None,
+                int(n_start), -1 if n_max is None else int(n_max), int(include_endpoints), free.ctypes.data, first.ctypes.data,
+                _stream(self.device)), "abstract_query_edges_host")
+        return free.view(np.bool_), first
+
+
 class SceneBackend:
     """Primitive scene with per-mode slots (one compiled blob per mode)."""
 

@@ -54,6 +54,11 @@ struct mrb200_scene {
 struct mrb200_abstract {
     mrb::AbstractSceneData data;
     int* counter = nullptr;
+    // mapped pinned staging of the host-buffer queries (mrb200_abstract_query_*_host), guarded by `mu`
+    std::mutex mu;
+    unsigned char* stage_pin = nullptr;
+    unsigned char* stage_pin_dev = nullptr;
+    size_t stage_bytes = 0;
 };
 
 extern "C" {
@@ -107,6 +112,7 @@ int mrb200_abstract_create(int n_agents, int dim, const double* radii, int n_sph
 int mrb200_abstract_destroy(mrb200_abstract_t* env) {
     if (!env) return MRB200_OK;
     cudaFree(env->counter);
+    cudaFreeHost(env->stage_pin);
     delete env;
     return MRB200_OK;
 }
@@ -131,6 +137,68 @@ int mrb200_abstract_check_edges(const mrb200_abstract_t* env, const double* q1, 
                                                free_dev, first_pos_dev, env->counter, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "abstract_check_edges");
     g_launches++;
+    return MRB200_OK;
+}
+
+static int abstract_stage(mrb200_abstract_t* env, size_t bytes, cudaStream_t st) {
+    if (bytes <= env->stage_bytes) return MRB200_OK;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "abstract query: sync");
+    cudaFreeHost(env->stage_pin);
+    env->stage_pin = env->stage_pin_dev = nullptr;
+    env->stage_bytes = 0;
+    size_t cap = 4096;
+    while (cap < bytes) cap *= 2;
+    e = cudaHostAlloc(&env->stage_pin, cap, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&env->stage_pin_dev, env->stage_pin, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "abstract query: cudaHostAlloc");
+    env->stage_bytes = cap;
+    return MRB200_OK;
+}
+
+int mrb200_abstract_query_configs_host(mrb200_abstract_t* env, const double* q_host, int64_t B, uint8_t* free_host,
+                                       mrb200_stream_t stream) {
+    if (!env || B < 0 || (B && (!q_host || !free_host))) return fail(MRB200_ERR_ARG, "abstract_query_configs_host: bad argument");
+    if (B == 0) return MRB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lock(env->mu);
+    const size_t D = (size_t)env->data.n_agents * env->data.dim;
+    const size_t qb = ((size_t)B * D * 8 + 15) & ~size_t(15);
+    int rc = abstract_stage(env, qb + (size_t)B, st);
+    if (rc) return rc;
+    memcpy(env->stage_pin, q_host, (size_t)B * D * 8);
+    rc = mrb200_abstract_check_configs(env, (const double*)env->stage_pin_dev, B, env->stage_pin_dev + qb, stream);
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "abstract_query_configs_host");
+    memcpy(free_host, env->stage_pin + qb, (size_t)B);
+    return MRB200_OK;
+}
+
+int mrb200_abstract_query_edges_host(mrb200_abstract_t* env, const double* q1_host, const double* q2_host, int64_t E,
+                                     double resolution, const int32_t* N_host, int32_t n_start, int32_t n_max,
+                                     int include_endpoints, uint8_t* free_host, int32_t* first_pos_host, mrb200_stream_t stream) {
+    if (!env || E < 0 || (E && (!q1_host || !q2_host || !free_host)))
+        return fail(MRB200_ERR_ARG, "abstract_query_edges_host: bad argument");
+    if (E == 0) return MRB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lock(env->mu);
+    const size_t D = (size_t)env->data.n_agents * env->data.dim;
+    const size_t qb = ((size_t)E * D * 8 + 15) & ~size_t(15), nb = ((size_t)E * 4 + 15) & ~size_t(15);
+    int rc = abstract_stage(env, 2 * qb + 2 * nb + (size_t)E, st);   // q1 | q2 | N | first | free
+    if (rc) return rc;
+    memcpy(env->stage_pin, q1_host, (size_t)E * D * 8);
+    memcpy(env->stage_pin + qb, q2_host, (size_t)E * D * 8);
+    if (N_host) memcpy(env->stage_pin + 2 * qb, N_host, (size_t)E * 4);
+    unsigned char* d = env->stage_pin_dev;
+    rc = mrb200_abstract_check_edges(env, (const double*)d, (const double*)(d + qb), E, resolution,
+                                     N_host ? (const int32_t*)(d + 2 * qb) : nullptr, n_start, n_max, include_endpoints,
+                                     d + 2 * qb + 2 * nb, (int32_t*)(d + 2 * qb + nb), stream);
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "abstract_query_edges_host");
+    if (first_pos_host) memcpy(first_pos_host, env->stage_pin + 2 * qb + nb, (size_t)E * 4);
+    memcpy(free_host, env->stage_pin + 2 * qb + 2 * nb, (size_t)E);
     return MRB200_OK;
 }
 

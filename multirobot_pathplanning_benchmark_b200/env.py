@@ -644,12 +644,19 @@ if HAVE_REFERENCE:
         def __deepcopy__(self, memo):
             return self  # immutable device-side scene: environment copies share it
 
+        SMALL = 64   # queries up to this size take the host-buffer entry points (one library call, no torch tensors)
+
         def check_configs(self, q):
             t = self.torch
-            return self.be.check_configs(t.from_numpy(np.ascontiguousarray(q, np.float64)).cuda()).cpu().numpy()
+            q = np.ascontiguousarray(q, np.float64)
+            if len(q) <= self.SMALL:
+                return self.be.query_configs_host(q)
+            return self.be.check_configs(t.from_numpy(q).cuda()).cpu().numpy()
 
         def check_edges(self, q1, q2, resolution, N=None, n_start=0, n_max=None, include_endpoints=False):
             t = self.torch
+            if len(q1) <= self.SMALL:
+                return self.be.query_edges_host(q1, q2, resolution, N=N, n_start=n_start, n_max=n_max, include_endpoints=include_endpoints)
             Nt = None if N is None else t.from_numpy(np.ascontiguousarray(N, np.int32)).cuda()
             f, p = self.be.check_edges(t.from_numpy(np.ascontiguousarray(q1, np.float64)).cuda(),
                                        t.from_numpy(np.ascontiguousarray(q2, np.float64)).cuda(), resolution, N=Nt, n_start=n_start,

@@ -79,3 +79,23 @@ def test_higher_dimensional_abstract_env(cuda_lib):
     got = be.check_configs(torch.from_numpy(q).cuda()).cpu().numpy()
     assert np.array_equal(got, sc.batch_flags(q))
     assert 0.02 < got.mean() < 0.98
+
+
+def test_host_buffer_queries_are_bit_exact_too(backend):
+    """mrb200_abstract_query_*_host (single-query seam, mapped pinned staging) against the device-buffer calls and the oracle"""
+    sc = OA.AbstractScene.abstract_test()
+    rng = np.random.default_rng(8)
+    q = rng.uniform(-2, 2, (500, 4))
+    want = sc.batch_flags(q)
+    assert np.array_equal(backend.query_configs_host(q), want)
+    for i in range(0, 500, 37):
+        assert backend.query_configs_host(q[i:i + 1])[0] == want[i]
+    q2 = q + rng.uniform(-1, 1, q.shape)
+    for kw in ({}, {"n_start": 3, "n_max": 11}, {"include_endpoints": True}):
+        f, p = backend.query_edges_host(q, q2, 0.01, **kw)
+        of, op = sc.batch_edge_flags(q, q2, 0.01, include_endpoints=kw.get("include_endpoints", False),
+                                     N_start=kw.get("n_start", 0), N_max=kw.get("n_max"))
+        assert np.array_equal(f, of) and np.array_equal(p, op)
+    f1, p1 = backend.query_edges_host(q[:1], q2[:1], 0.01, N=np.array([40], np.int32))
+    of, op = sc.batch_edge_flags(q[:1], q2[:1], 0.01, Ns=np.array([40]))
+    assert f1[0] == of[0] and p1[0] == op[0]
