@@ -51,4 +51,4 @@ if t:
         cpu = v.get("cpu_port_median_s")
         print(f"| {s} ({v.get('modes', '?')} modes, {v['samples_per_mode']} samples/mode) | {v['b200_median_s']:.3f} | {cpu if cpu is None else round(cpu, 2)} | "
               f"{'' if cpu is None else str(round(cpu / v['b200_median_s'])) + 'x'} |")
-print("\nMulti-GPU: profiles/r1_scaling.md.  Kernel profiles: profiles/r1_check_configs_v3_*.txt, r1_check_edges_v3.txt.")
+print("\nMulti-GPU: profiles/r1_scaling.md.  Kernel profiles: profiles/r1_check_configs_v3_*.txt, r1_check_edges_v4.txt.")
