@@ -283,6 +283,8 @@ if HAVE_REFERENCE:
             self.manipulating_env = False
             self.prev_mode = None
             self._slot = None
+            self._mask_cache: Dict[tuple, tuple] = {}
+            self._slot_by_mode: Dict[Optional[int], int] = {}
             super().__init__()
             self.spec = ProblemSpec(agent_type=AgentType.MULTI_AGENT, constraints=ConstraintType.UNCONSTRAINED,
                                     manipulation=ManipulationType.MANIPULATION, dependency=DependencyType.FULLY_ORDERED,
@@ -339,7 +341,13 @@ if HAVE_REFERENCE:
         def set_to_mode(self, m: "Mode", config=None, use_cached: bool = True, place_in_cache: bool = True):
             if m is self.prev_mode and self._slot is not None:
                 return
-            self._slot = self._slot_for_mode(m)
+            # Mode.id is unique per mode object (planning_env.py:139-140): the replay of the mode chain runs once per
+            # mode, like the per-mode cache of rai_env.set_to_mode (rai_base_env.py:816-828)
+            mid = None if m is None else m.id
+            slot = self._slot_by_mode.get(mid)
+            if slot is None:
+                slot = self._slot_by_mode[mid] = self._slot_for_mode(m)
+            self._slot = slot
             self.prev_mode = m
 
         def get_scenegraph_info_for_mode(self, mode: "Mode", is_start_mode: bool = False):
@@ -403,16 +411,20 @@ if HAVE_REFERENCE:
             return self._one_config(np.asarray(q, np.float32)[None], collision_tolerance)
 
         def _robot_masks(self, robots: List[str], m: "Mode"):
-            cs = self.model.compiled(self._slot)
             frames = set()
             for r in robots:
                 t = self.tasks[m.task_ids[self.robots.index(r)]]
                 if t.frames is not None:
                     frames.update(t.frames)
-            others = [r for r in self.robots if r not in robots]
-            rel = np.array([any(r in n for r in robots) or n in frames for n in cs.shape_names], np.uint8)
-            oth = np.array([any(o in n for o in others) for n in cs.shape_names], np.uint8)
-            return rel, oth
+            key = (self._slot, tuple(robots), tuple(sorted(frames)))
+            hit = self._mask_cache.get(key)
+            if hit is None:   # (the substring tests over all shape names are the same for every query of this kind)
+                cs = self.model.compiled(self._slot)
+                others = [r for r in self.robots if r not in robots]
+                rel = np.array([any(r in n for r in robots) or n in frames for n in cs.shape_names], np.uint8)
+                oth = np.array([any(o in n for o in others) for n in cs.shape_names], np.uint8)
+                hit = self._mask_cache[key] = (rel, oth)
+            return hit
 
         def is_collision_free_for_robot(self, r, q, m=None, collision_tolerance=None, set_mode: bool = True) -> bool:
             """rai_base_env.py:515-615: free unless the total penetration exceeds the tolerance AND some
