@@ -794,8 +794,9 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(E
                     }
                 }
             }
+            __syncwarp();  // warp 0 goes straight on to refill and hand out the next tile; the others wait at the
+                           // barrier that follows it (no CTA-wide barrier needed here: only warp 0 touches the slots)
         }
-        __syncthreads();
     }
 }
 
