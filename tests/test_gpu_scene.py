@@ -194,3 +194,61 @@ def test_host_buffer_queries_equal_device_buffer_calls(be):
     assert be.query_configs_host(slot, q[:0]).shape == (0,)
     with pytest.raises(Exception):
         be.query_configs_host(slot, q[:, :5])
+
+
+def test_edge_kernel_corner_cases(be):
+    """multi-edge tiles: degenerate edges (N = 2: no interior point), empty windows, a single edge, mixed explicit N,
+    windows beyond N, batches smaller than one tile and far larger than the grid -- all against the oracle"""
+    slot, sc, cs, kw = be.scenes["2d_handover"]
+    rng = np.random.default_rng(12)
+    lim = sc.limits()
+
+    def both(q1, q2, **kwargs):
+        f, p = be.check_edges(slot, torch.from_numpy(q1).cuda(), torch.from_numpy(q2).cuda(), 0.01,
+                              **{k: (torch.from_numpy(v).cuda() if k == "N" else v) for k, v in kwargs.items()})
+        okw = dict(kwargs)
+        if "N" in okw:
+            okw["Ns"] = okw.pop("N")
+        if okw.get("n_max") is None:
+            okw.pop("n_max", None)
+        of, op, _ = O.check_edges(cs.blob64, q1.astype(np.float64), q2.astype(np.float64), 0.01, **okw)
+        return f.cpu().numpy(), p.cpu().numpy(), of, op
+
+    free_q = uniform_configs(sc, 20000, 40)
+    free_q = free_q[be.check_configs(slot, torch.from_numpy(free_q).cuda()).cpu().numpy().astype(bool)]
+    # (1) identical endpoints and sub-resolution moves: N = 2, nothing to check -> free, first = -1
+    q1 = free_q[:300]
+    q2 = q1 + rng.uniform(-0.004, 0.004, q1.shape).astype(np.float32)
+    f, p, of, op = both(q1, q2)
+    assert f.all() and (p == -1).all() and np.array_equal(f, of) and np.array_equal(p, op)
+    # ... but with include_endpoints the two endpoints are checked
+    f, p, of, op = both(q1, q2, include_endpoints=True)
+    assert np.array_equal(f, of) and np.array_equal(p, op)
+    # (2) a single edge, and a batch of 33 edges (one more than a tile)
+    for n in (1, 33):
+        a = free_q[:n]
+        b = free_q[1000:1000 + n]
+        f, p, of, op = both(a, b)
+        assert (f == of).all() and np.array_equal(p[f == of], op[f == of])
+    # (3) explicit N of wildly different sizes in one batch, including the minimum
+    n = 2000
+    a, b = free_q[:n], free_q[2000:2000 + n]
+    N = rng.choice([2, 3, 5, 31, 32, 33, 64, 700], n).astype(np.int32)
+    f, p, of, op = both(a, b, N=N)
+    assert (f == of).mean() > 0.995 and np.array_equal(p[f == of], op[f == of])
+    # (4) windows: empty (n_start = n_max), beyond the end, and a late start
+    for ns, nm in ((5, 5), (0, 100000), (40, None), (3, 4)):
+        f, p, of, op = both(a, b, N=N, n_start=ns, n_max=nm)
+        assert (f == of).mean() > 0.995 and np.array_equal(p[f == of], op[f == of]), (ns, nm)
+        if ns == nm:
+            assert f.all() and (p == -1).all()
+    # (5) far more edges than resident CTAs x slots, all short: every edge gets exactly one answer
+    big = 300_000
+    a = free_q[rng.integers(0, len(free_q), big)]
+    b = a + rng.uniform(-0.05, 0.05, a.shape).astype(np.float32)
+    fl = torch.full((big,), 9, dtype=torch.uint8, device="cuda")
+    f, p = be.check_edges(slot, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), 0.01)
+    assert f.shape == (big,) and set(np.unique(f.cpu().numpy())) <= {0, 1}
+    sub = rng.integers(0, big, 3000)
+    of, op, _ = O.check_edges(cs.blob64, a[sub].astype(np.float64), b[sub].astype(np.float64), 0.01)
+    assert (f.cpu().numpy()[sub] == of).mean() > 0.995
