@@ -56,3 +56,23 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "liboracle" not in txt, f
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/mrb200.h is the drop-in boundary: it must compile as C99 (no C++, no torch types) and every call a C
+    host would make must link against libmrb200.so"""
+    import subprocess
+    lib = build.build()
+    src = tmp_path / "host.c"
+    src.write_text('#include "mrb200.h"\n#include <stddef.h>\n'
+                   'int main(void) {\n'
+                   '  mrb200_scene_t* s = NULL;\n'
+                   '  int rc = mrb200_scene_create(0, &s);            /* bad argument: must fail without a device, too */\n'
+                   '  return (mrb200_version() > 0 && rc == MRB200_ERR_ARG && mrb200_last_error()[0] != 0) ? 0 : 1;\n'
+                   '}\n')
+    exe = tmp_path / "host"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    libdir = os.path.dirname(lib)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-L", libdir, "-lmrb200",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True, capture_output=True)
+    assert subprocess.run([str(exe)]).returncode == 0
