@@ -248,6 +248,47 @@ class SceneModel:
     def scene(self, slot: int) -> Scene:
         return self._scenes[slot]
 
+    def sample_informed(self, slot: int, n: int, focal_points: np.ndarray, cost_bound: float, metric: str = "euclidean",
+                        reduction: str = "max", rng: Optional[np.random.RandomState] = None, max_rounds: int = 64):
+        """The planners' informed rejection loop in whole batches (P/planners/composite_prm_planner.py:180-227: a
+        uniform sample is kept only if cost(start focus, q) + cost(q, goal focus) <= the incumbent cost, and only
+        then collision checked).  Both costs are evaluated on the device for the whole batch
+        (mrb200_batch_cost: the reference's per-robot metric and reduction), the ellipse test compacts the batch, and
+        only the survivors reach the FK + narrowphase kernel.
+        -> (collision-free configurations inside the ellipse [<= n, D] fp64, samples drawn, samples pruned by the ellipse)"""
+        import torch
+        from . import knn as K
+        rng = rng or np.random
+        dev = self.device.dev
+        gen = torch.Generator(device=dev).manual_seed(int(rng.randint(0, 2 ** 31 - 1)))  # samples are drawn on the device
+        lim = self.base.limits()
+        lo = torch.from_numpy(lim[0].astype(np.float32)).to(dev)
+        width = torch.from_numpy((lim[1] - lim[0]).astype(np.float32)).to(dev)
+        rs = self.base.robot_slices()
+        sl = [list(rs[r]) for r in self.base.robots]
+        f0 = torch.from_numpy(np.asarray(focal_points[0], np.float64)).to(dev)
+        f1 = torch.from_numpy(np.asarray(focal_points[1], np.float64)).to(dev)
+        out, have, drawn, pruned = [], 0, 0, 0
+        batch = max(1024, 4 * n)
+        for _ in range(max_rounds):
+            qd = lo + width * torch.rand((batch, lim.shape[1]), generator=gen, device=dev, dtype=torch.float32)
+            q64 = qd.double()
+            cost = K.batch_config_cost(f0, q64, sl, metric, reduction) + K.batch_config_cost(f1, q64, sl, metric, reduction)
+            keep = cost <= cost_bound
+            drawn += batch
+            pruned += int(batch - keep.sum().item())
+            cand = qd[keep].contiguous()
+            if cand.shape[0]:
+                ok = self.device.check_configs(slot, cand).bool()
+                good = cand[ok].double().cpu().numpy()
+                out.append(good)
+                have += len(good)
+            if have >= n:
+                break
+            batch = min(2 * batch, 1 << 22)
+        res = np.concatenate(out)[:n] if out else np.zeros((0, lim.shape[1]))
+        return res, drawn, pruned
+
     # batch API (arrays or CUDA tensors in, device results out)
     def check_configs(self, slot, qs, tol=None):
         return self.device.check_configs(slot, qs, tol)
@@ -509,6 +550,12 @@ if HAVE_REFERENCE:
             if len(res) < n:
                 raise RuntimeError("could not find enough collision-free configurations")
             return res
+
+        def sample_valid_informed_batch(self, mode, n: int, focal_points: np.ndarray, cost_bound: float,
+                                        rng: Optional[np.random.RandomState] = None):
+            """informed rejection sampling in whole batches, see SceneModel.sample_informed"""
+            self.set_to_mode(mode)
+            return self.model.sample_informed(self._slot, n, focal_points, cost_bound, self.cost_metric, self.cost_reduction, rng)
 
         # ---- additive batch variants (arrays or CUDA tensors in, device tensors out) -----------
         def batch_is_collision_free(self, qs, mode):

@@ -252,3 +252,33 @@ def test_edge_kernel_corner_cases(be):
     sub = rng.integers(0, big, 3000)
     of, op, _ = O.check_edges(cs.blob64, a[sub].astype(np.float64), b[sub].astype(np.float64), 0.01)
     assert (f.cpu().numpy()[sub] == of).mean() > 0.995
+
+
+def test_informed_batch_sampler_prunes_on_the_device(cuda_lib):
+    """ellipse prune (two batch_config_cost evaluations on the device) before the collision kernel:
+    every returned configuration is inside the ellipse, collision free per the oracle, and the prune really happens"""
+    from multirobot_pathplanning_benchmark_b200.env import SceneModel
+    from oracle import oracle_abstract as OA
+    mk, kw = SCENES["box_rearrangement"]
+    sc = mk()
+    model = SceneModel(sc, kw["tol"], kw["resolution"])
+    slot = model.slot_for(())
+    home = sc.home()
+    goal = home.copy()
+    goal[:6] += np.array([0.8, 0.5, -0.6, 0.4, 0.3, -0.5])
+    sl = np.array([list(sc.robot_slices()[r]) for r in sc.robots])
+    direct = OA.batch_config_cost((goal - home)[None], sl, "euclidean", "max")[0]
+    bound = 5.0 * direct
+    q, drawn, pruned = model.sample_informed(slot, 500, np.stack([home, goal]), bound, "euclidean", "max", np.random.RandomState(3))
+    assert len(q) == 500 and pruned > 0.5 * drawn           # most of the box lies outside the ellipse
+    assert drawn < 3e8
+    c = OA.batch_config_cost(q - home[None], sl, "euclidean", "max") + OA.batch_config_cost(q - goal[None], sl, "euclidean", "max")
+    assert (c <= bound * (1 + 1e-12)).all()
+    cs = model.compiled(slot)
+    ofree, open_, omind = O.check_configs(cs.blob64, q)
+    clear = np.abs(O.margin(open_, omind, cs.tol)) > MARGIN
+    assert ofree[clear].all()
+    # an ellipse that cannot contain anything returns nothing (and says how much it drew)
+    q0, drawn0, pruned0 = model.sample_informed(slot, 10, np.stack([home, goal]), 0.5 * direct, "euclidean", "max",
+                                                np.random.RandomState(4), max_rounds=2)
+    assert len(q0) == 0 and pruned0 == drawn0
