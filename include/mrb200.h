@@ -113,6 +113,16 @@ int mrb200_query_edges_host(mrb200_scene_t* scene, int slot, const float* q1_hos
                             mrb200_stream_t stream);
 /* introspection of a slot: D, n_shapes, n_pairs (dynamic), shared memory bytes per CTA */
 int mrb200_scene_info(const mrb200_scene_t* scene, int slot, int32_t* out4);
+/* Large plain batches (mrb200_check_configs, B >= 4096, no penetration output) can run as two-phase tiles: a cheap
+ * lower bound of the penetration against the large static boxes (table, floor) retires most colliding
+ * configurations after FK; the undecided ones are pooled and evaluated exactly as by the single-pass kernel, so
+ * flags are the same either way.  It pays when the bound decides more than about half of the batch, which depends
+ * on the caller's inputs: by default the first large batches on a slot measure it and the slot settles on one
+ * kernel.  policy: 0 = measure and settle (default, also resets the measurement), 1 = always two-phase,
+ * 2 = always single pass.  mrb200_scene_get_two_phase: out3 = {policy / settled state (0 measuring, 1 two-phase,
+ * 2 single pass), configurations seen while measuring, of those decided by the bound}. */
+int mrb200_scene_set_two_phase(mrb200_scene_t* scene, int slot, int policy);
+int mrb200_scene_get_two_phase(const mrb200_scene_t* scene, int slot, int32_t* out3);
 
 /* ---- distances and neighbour search: batch_config_dist (P/problems/core/configuration.py:303-349),
  * PRM get_neighbors (P/planners/prm/prm_graph.py:389-549), RRT* near (P/planners/rrtstar_base.py:

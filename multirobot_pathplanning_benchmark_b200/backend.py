@@ -158,6 +158,20 @@ class SceneBackend:
         _lib.check(self.lib.mrb200_scene_info(self.handle, int(slot), out), "scene_info")
         return {"D": out[0], "n_shapes": out[1], "n_pairs": out[2], "smem_bytes": out[3]}
 
+    TWO_PHASE_POLICIES = {"auto": 0, "always": 1, "never": 2}
+
+    def set_two_phase(self, slot: int, policy: str = "auto") -> None:
+        """Kernel choice for large plain batches on this slot: "auto" (measure what the table / floor bound decides on
+        the first large batches, then settle), "always" or "never" (two-phase tiles).  Flags do not depend on it."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mrb200_scene_set_two_phase(self.handle, int(slot), self.TWO_PHASE_POLICIES[policy]),
+                       "scene_set_two_phase")
+
+    def two_phase_info(self, slot: int):
+        out = (C.c_int32 * 3)()
+        _lib.check(self.lib.mrb200_scene_get_two_phase(self.handle, int(slot), out), "scene_get_two_phase")
+        return {"state": ("measuring", "two_phase", "single_pass")[out[0]], "seen": out[1], "decided_by_bound": out[2]}
+
     def _q(self, slot, q, name="q"):
         q = _require_cuda(q, torch.float32, name)
         D = self.compiled[slot].dof

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -35,6 +36,12 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct ModeSlot {
     uint32_t* blob = nullptr;  // device
     int words = 0, D = 0, world_words = 0, n_shapes = 0, n_pairs = 0;
+    int n_large = 0;           // pairs against large static boxes (table, floor): phase A of the two-phase tiles
+    // two-phase tiles pay off when phase A decides most configurations; that depends on the caller's inputs, so the
+    // first large batches measure it (device counters copied to pinned memory behind the launch, read without
+    // a synchronisation by a later call): 0 = measuring, 1 = keep, 2 = single-pass kernel from now on
+    mutable int two_phase_state = 0;
+    bool two_phase_forced = false;   // set through mrb200_scene_set_two_phase: no measuring
 };
 
 }  // namespace
@@ -42,6 +49,8 @@ struct ModeSlot {
 struct mrb200_scene {
     std::vector<ModeSlot> slots;
     int* counter = nullptr;  // device scratch for the edge scheduler
+    int* stats_dev = nullptr;   // [2 * slots] (configurations seen, decided in phase A) per mode slot
+    int* stats_pin = nullptr;   // pinned copy, refreshed behind two-phase launches while a slot is still measuring
     // staging of the host-buffer query entry points (mrb200_query_*_host): one device and one pinned host
     // buffer, grown on demand, guarded by `mu`
     std::mutex mu;
@@ -212,10 +221,16 @@ int mrb200_scene_create(int max_modes, mrb200_scene_t** out) {
     auto* sc = new mrb200_scene();
     sc->slots.resize(max_modes);
     e = cudaMalloc(&sc->counter, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&sc->stats_dev, 2 * sizeof(int) * max_modes);
+    if (e == cudaSuccess) e = cudaMemset(sc->stats_dev, 0, 2 * sizeof(int) * max_modes);
+    if (e == cudaSuccess) e = cudaHostAlloc(&sc->stats_pin, 2 * sizeof(int) * max_modes, cudaHostAllocDefault);
     if (e != cudaSuccess) {
+        cudaFree(sc->counter);
+        cudaFree(sc->stats_dev);
         delete sc;
         return cuda_fail(e, "scene_create");
     }
+    memset(sc->stats_pin, 0, 2 * sizeof(int) * max_modes);
     *out = sc;
     return MRB200_OK;
 }
@@ -224,6 +239,8 @@ int mrb200_scene_destroy(mrb200_scene_t* sc) {
     if (!sc) return MRB200_OK;
     for (auto& s : sc->slots) cudaFree(s.blob);
     cudaFree(sc->counter);
+    cudaFree(sc->stats_dev);
+    cudaFreeHost(sc->stats_pin);
     cudaFree(sc->stage_dev);
     cudaFreeHost(sc->stage_pin);
     delete sc;
@@ -258,7 +275,15 @@ int mrb200_scene_set_mode(mrb200_scene_t* sc, int slot, const void* blob_host, s
     s.n_shapes = n_shapes;
     s.n_pairs = 0;
     for (int t = 0; t < MRB_NUM_PAIR_TYPES; t++) s.n_pairs += (int)h[MRB_H_N_PAIRS + t];
-    if (mrb::scene_smem_bytes(s.words, s.D, s.world_words, s.n_shapes) > 227 * 1024)
+    s.n_large = 0;
+    for (int t = 0; t < MRB_NUM_PAIR_TYPES; t++) s.n_large += (int)h[MRB_H_BP + (t * MRB_BP_SUBLISTS + 2) * 2 + 1];
+    s.two_phase_state = 0;
+    s.two_phase_forced = false;
+    sc->stats_pin[2 * slot] = sc->stats_pin[2 * slot + 1] = 0;
+    e = cudaMemsetAsync(sc->stats_dev + 2 * slot, 0, 2 * sizeof(int), st);
+    if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: counters");
+    if (mrb::scene_smem_bytes(s.words, s.D, s.world_words, s.n_shapes, 1) > 227 * 1024 ||
+        mrb::scene_smem_bytes(s.words, s.D, s.world_words, s.n_shapes, 2) > 227 * 1024)
         return fail(MRB200_ERR_ARG, "scene_set_mode: scene needs more than 227 KB of shared memory per CTA");
     e = mrb::launch_static_penetration(s.blob, st);
     if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: static pairs");
@@ -278,6 +303,29 @@ int mrb200_scene_info(const mrb200_scene_t* sc, int slot, int32_t* out4) {
     out4[1] = s->n_shapes;
     out4[2] = s->n_pairs;
     out4[3] = (int32_t)mrb::scene_smem_bytes(s->words, s->D, s->world_words, s->n_shapes);
+    return MRB200_OK;
+}
+
+int mrb200_scene_set_two_phase(mrb200_scene_t* sc, int slot, int policy) {
+    if (!get_slot(sc, slot) || policy < 0 || policy > 2) return fail(MRB200_ERR_ARG, "scene_set_two_phase: bad argument");
+    ModeSlot& s = sc->slots[slot];
+    s.two_phase_state = policy;
+    s.two_phase_forced = policy != 0;
+    if (policy == 0) {
+        cudaError_t e = cudaDeviceSynchronize();  // a counter copy of an earlier launch may still be in flight
+        if (e == cudaSuccess) e = cudaMemset(sc->stats_dev + 2 * slot, 0, 2 * sizeof(int));
+        if (e != cudaSuccess) return cuda_fail(e, "scene_set_two_phase");
+        sc->stats_pin[2 * slot] = sc->stats_pin[2 * slot + 1] = 0;
+    }
+    return MRB200_OK;
+}
+
+int mrb200_scene_get_two_phase(const mrb200_scene_t* sc, int slot, int32_t* out3) {
+    const ModeSlot* s = get_slot(sc, slot);
+    if (!s || !out3) return fail(MRB200_ERR_ARG, "scene_get_two_phase: empty slot");
+    out3[0] = s->two_phase_state;
+    out3[1] = sc->stats_pin[2 * slot];
+    out3[2] = sc->stats_pin[2 * slot + 1];
     return MRB200_OK;
 }
 
@@ -304,7 +352,27 @@ static int check_configs_impl(const mrb200_scene_t* sc, int slot, const float* q
     p.full_eval = full_eval;
     p.bulk_ok = allow_bulk && (((uintptr_t)q) & 15) == 0 && ((s->D * 4 * 32) % 16 == 0);
     p.rule = rule;
+    // Two-phase tiles: small batches leave nothing to pool; otherwise the first large batches measure what phase A
+    // decides (state 0) and the slot settles on one kernel.  MRB200_TWO_PHASE=0 / 1 forces the choice (measurement aid).
+    static const int forced = [] { const char* v = getenv("MRB200_TWO_PHASE"); return v ? (v[0] == '1' ? 1 : 0) : -1; }();
+    const bool eligible = s->n_large > 0 && B >= 4096 && !pen_dev && !full_eval && !rule.enabled;
+    bool measuring = false;
+    if (eligible && forced < 0) {
+        if (s->two_phase_state == 0 && !s->two_phase_forced) {
+            const volatile int* st2 = sc->stats_pin + 2 * slot;
+            const int seen = st2[0], decided = st2[1];
+            if (seen >= 4096) s->two_phase_state = (int64_t)decided * 20 >= (int64_t)seen * 11 ? 1 : 2;
+        }
+        p.two_phase = s->two_phase_state != 2;
+        measuring = s->two_phase_state == 0 && !s->two_phase_forced;
+    } else {
+        p.two_phase = eligible && forced == 1;
+    }
+    p.stats = measuring ? sc->stats_dev + 2 * slot : nullptr;
     cudaError_t e = mrb::launch_check_configs(p, (cudaStream_t)stream);
+    if (e == cudaSuccess && measuring)
+        e = cudaMemcpyAsync(sc->stats_pin + 2 * slot, sc->stats_dev + 2 * slot, 2 * sizeof(int), cudaMemcpyDeviceToHost,
+                            (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "check_configs");
     g_launches++;
     return MRB200_OK;

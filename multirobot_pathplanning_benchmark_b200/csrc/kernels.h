@@ -23,6 +23,8 @@ struct ConfigParams {
     float* pen_out;   // device [B] or null
     int full_eval;    // 1: no early exit (pen_out is then the complete sum)
     int bulk_ok;      // q is 16-byte aligned: tiles may be fetched with cp.async.bulk
+    int two_phase;    // 1: two-phase tiles (pairs against the table / floor first, pooled survivors for the rest)
+    int* stats;       // device [2] or null: two-phase kernels add (configurations seen, decided in phase A)
     RobotRule rule;
 };
 
@@ -41,7 +43,7 @@ struct EdgeParams {
     int* counter;         // device scratch: dynamic edge scheduler
 };
 
-size_t scene_smem_bytes(int blob_words, int D, int world_words, int n_shapes, bool edges = true);
+size_t scene_smem_bytes(int blob_words, int D, int world_words, int n_shapes, int kind = 1);  // 0 configs, 1 edges, 2 two-phase configs
 cudaError_t launch_static_penetration(uint32_t* blob, cudaStream_t st);
 cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st);
 cudaError_t launch_check_edges(const EdgeParams& p, cudaStream_t st);

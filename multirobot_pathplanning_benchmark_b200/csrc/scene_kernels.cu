@@ -48,16 +48,23 @@ struct Smem {
     uint32_t* queue;   // [WARPS][QCAP] surviving (configuration, pair) items
     uint8_t* sflag;  // [n_shapes] bit0 = relevant, bit1 = other robot (A6 rule)
     uint64_t* bar;   // [3] mbarriers: blob, q0, q1
-    int* misc;       // [EDGE_MISC] edge kernel bookkeeping (active edge slots, lane assignment)
-    double* ed;      // [EDGE_SLOTS][2*D] start and step of the active edges (fp64)
+    int* misc;       // edge kernel: [EDGE_MISC] bookkeeping (active edge slots, lane assignment);
+                     // configuration kernel: [CFG_MISC] survivor pool bookkeeping
+    double* ed;      // edge kernel: [EDGE_SLOTS][2*D] start and step of the active edges (fp64);
+                     // configuration kernel: [TILE][D] floats, the pooled survivors' configurations
 };
 
 constexpr int EDGE_SLOTS = 8;    // edges a CTA keeps in flight (refill maps 4 lanes to a slot: 8 x 4 = one warp): short edges share one tile of 32 interpolation points
 constexpr int EDGE_MISC = 8 * EDGE_SLOTS + 2 * 32 + 8;
+// configuration kernel, two-phase tiles: [0..63] pool slot -> configuration index (int64 x 32), [64..95] lane -> pool
+// slot of the current tile, [96..103] control words
+constexpr int CFG_MISC = 64 + 32 + 8;
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-__host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_words, int n_shapes, bool edges, size_t* off) {
+// kind: 0 = configuration kernel (single pass), 1 = edge kernel, 2 = configuration kernel with two-phase tiles
+__host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_words, int n_shapes, int kind, size_t* off) {
+    const bool edges = kind == 1, pool = kind == 2;
     size_t o = 0;
     off[0] = o; o = align16(o + size_t(blob_words) * 4);
     off[1] = o; o = align16(o + size_t(TILE) * D * 4);
@@ -67,14 +74,14 @@ __host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_w
     off[5] = o; o = align16(o + size_t(MAX_WARPS) * 64 * 4);
     off[6] = o; o = align16(o + size_t(n_shapes));
     off[7] = o; o = align16(o + 3 * 8);
-    off[8] = o; o = align16(o + (edges ? EDGE_MISC * 4 : 0));  // the configuration kernel carries no edge state
-    off[9] = o; o = align16(o + (edges ? size_t(EDGE_SLOTS) * 2 * D * 8 : 0));
+    off[8] = o; o = align16(o + (edges ? EDGE_MISC * 4 : pool ? CFG_MISC * 4 : 0));
+    off[9] = o; o = align16(o + (edges ? size_t(EDGE_SLOTS) * 2 * D * 8 : pool ? size_t(TILE) * D * 4 : 0));
     return o;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int blob_words, int D, int world_words, int n_shapes, bool edges) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int blob_words, int D, int world_words, int n_shapes, int kind) {
     size_t off[10];
-    smem_layout(blob_words, D, world_words, n_shapes, edges, off);
+    smem_layout(blob_words, D, world_words, n_shapes, kind, off);
     Smem s;
     s.blob = (uint32_t*)(base + off[0]);
     s.q[0] = (float*)(base + off[1]);
@@ -90,9 +97,9 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int blob_words, int D
     return s;
 }
 
-size_t scene_smem_bytes(int blob_words, int D, int world_words, int n_shapes, bool edges) {
+size_t scene_smem_bytes(int blob_words, int D, int world_words, int n_shapes, int kind) {
     size_t off[10];
-    return smem_layout(blob_words, D, world_words, n_shapes, edges, off);
+    return smem_layout(blob_words, D, world_words, n_shapes, kind, off);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -552,6 +559,63 @@ __device__ __forceinline__ float process_tile(const Smem& sm, const float* q_til
     return total;
 }
 
+// Phase A of the two-phase tiles: FK, then a LOWER bound of the penetration against the large static boxes
+// (table, floor: broadphase sublist 2) from a few points of each moving core -- a point's centre, five
+// points of a segment, a box's centre.  For any point P of core X, d(X, Y) <= dist(P, core Y) - r_X - r_Y
+// (and every primitive routine returns at most -(r_X + r_Y) once the cores touch), so
+// sum max(0, r_X + r_Y - dist(P, core Y)) never exceeds the penetration the exact routines report.  No queue,
+// no narrowphase, no barrier but the two around the shared accumulator.  Warp 0 returns the bound per lane.
+template <int WARPS>
+__device__ __forceinline__ float table_phase(const Smem& sm, const float* q_tile, int D) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t* bi = sm.blob;
+    const float* bf = reinterpret_cast<const float*>(bi);
+    if (warp == WARPS - 1) sm.pen_fx[lane] = 0u;
+    fk_phase<WARPS>(bi, q_tile + lane * D, sm.W, warp, lane);
+    __syncthreads();
+    const char* Wl = reinterpret_cast<const char*>(sm.W + lane);
+    const int offS = bi[MRB_H_OFF_SHAPES], nmov = bi[MRB_H_NMOV];
+    float pen = 0.f;
+    for (int type = MRB_PT_POINT_BOX; type <= MRB_PT_BOX_BOX; ++type) {
+        const int n = bi[MRB_H_BP + (type * MRB_BP_SUBLISTS + 2) * 2 + 1];
+        if (n == 0) continue;
+        const int off = bi[MRB_H_BP + (type * MRB_BP_SUBLISTS + 2) * 2];
+        const uint2* rec = reinterpret_cast<const uint2*>(bi + off);
+        const int lo = (n * warp) / WARPS, hi = (n * (warp + 1)) / WARPS;
+        for (int i = lo; i < hi; ++i) {
+            const uint32_t rx = rec[i].x, pk = bi[off + 2 * n + i];
+            const float rsum = bf[offS + (int)(pk & 0xffff) * MRB_SHAPE_WORDS + 3] + bf[offS + (int)((pk >> 16) & 0xfff) * MRB_SHAPE_WORDS + 3];
+            const float* px = reinterpret_cast<const float*>(Wl + (rx & 0xffffu));
+            const float* B = bf + offS + (nmov + (int)(rx >> 16)) * MRB_SHAPE_WORDS + 4;  // c[3], R[9], half[3]
+            const float* R = B + 3;
+            const float x = px[0] - B[0], y = px[TILE] - B[1], z = px[2 * TILE] - B[2];
+            const float l0 = dot3(R[0], R[3], R[6], x, y, z), l1 = dot3(R[1], R[4], R[7], x, y, z), l2 = dot3(R[2], R[5], R[8], x, y, z);
+            float d2;
+            if (type == MRB_PT_SEG_BOX) {  // five points of the segment: midpoint + u * half vector
+                const float hx = px[3 * TILE], hy = px[4 * TILE], hz = px[5 * TILE];
+                const float h0 = dot3(R[0], R[3], R[6], hx, hy, hz), h1 = dot3(R[1], R[4], R[7], hx, hy, hz), h2 = dot3(R[2], R[5], R[8], hx, hy, hz);
+                d2 = 3.0e38f;
+#pragma unroll
+                for (int k = -2; k <= 2; ++k) {
+                    const float u = 0.5f * (float)k;
+                    const float a0 = fmaxf(fabsf(fmaf(u, h0, l0)) - B[12], 0.f), a1 = fmaxf(fabsf(fmaf(u, h1, l1)) - B[13], 0.f),
+                                a2 = fmaxf(fabsf(fmaf(u, h2, l2)) - B[14], 0.f);
+                    d2 = fminf(d2, dot3(a0, a1, a2, a0, a1, a2));
+                }
+            } else {
+                const float a0 = fmaxf(fabsf(l0) - B[12], 0.f), a1 = fmaxf(fabsf(l1) - B[13], 0.f), a2 = fmaxf(fabsf(l2) - B[14], 0.f);
+                d2 = dot3(a0, a1, a2, a0, a1, a2);
+            }
+            pen += fmaxf(rsum - sqrtf(d2), 0.f);
+        }
+    }
+    if (pen > 0.f) atomicAdd(&sm.pen_fx[lane], (unsigned)(fminf(pen, 60.f) * PEN_SCALE));  // rounded down
+    __syncthreads();
+    float total = 0.f;
+    if (warp == 0) total = reinterpret_cast<const float*>(bi)[MRB_H_STATIC_PEN] + (float)sm.pen_fx[lane] * (1.f / PEN_SCALE);
+    return total;
+}
+
 // common prologue: barriers, blob staging through TMA, A6 shape flags
 __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob, int blob_words, int n_shapes,
                                             const RobotRule& rr, int THREADS) {
@@ -578,10 +642,10 @@ __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob
 // ------------------------------------------------------------------------------------------
 // configuration batch kernel (A5 / A6 batch variant)
 // ------------------------------------------------------------------------------------------
-template <int WARPS>
+template <int WARPS, bool TWO_PHASE>
 __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel(ConfigParams p) {
     constexpr int THREADS = TILE * WARPS;
-    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, false);
+    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, TWO_PHASE ? 2 : 0);
     stage_scene(sm, p.blob, p.blob_words, p.n_shapes, p.rule, THREADS);
 
     const int D = p.D;
@@ -608,6 +672,57 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
         }
     };
 
+    if constexpr (!TWO_PHASE) {
+        uint32_t phase[2] = {0, 0};
+        int64_t tile = blockIdx.x;
+        if (tile < n_tiles) fetch(tile, 0);
+        for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int64_t next = tile + gridDim.x;
+            if (next < n_tiles) fetch(next, buf ^ 1);  // buffer buf^1 was released by the barrier closing iteration it-1
+            const int64_t first = tile * TILE;
+            const int nvalid = (int)min((int64_t)TILE, p.B - first);
+            if (nvalid == TILE && p.bulk_ok) {
+                mbar_wait(&sm.bar[1 + buf], phase[buf]);
+                phase[buf] ^= 1;
+            } else {
+                __syncthreads();
+            }
+            bool relpen = false;
+            const float total = process_tile<WARPS>(sm, sm.q[buf], D, tol, early, p.rule.enabled, &relpen);
+            if (warp == 0 && lane < nvalid) {
+                const bool coll = p.rule.enabled ? (total > tol && relpen) : (total > tol);
+                p.flags[first + lane] = coll ? 0 : 1;
+                if (p.pen_out) p.pen_out[first + lane] = total;
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    // Two-phase tiles (plain flag queries on scenes with a table / floor; the launcher picks this variant): phase A
+    // runs FK and a cheap lower bound of the penetration against the large static boxes (table_phase), which
+    // decides most colliding configurations; the undecided configurations of successive tiles are pooled (q and
+    // index) and complete single-pass tiles run on 32 survivors at a time, so their flags are computed exactly as
+    // by the single-pass kernel.  A CTA that sees few decisions in phase A falls back to single-pass tiles.
+    int64_t* pool_idx = reinterpret_cast<int64_t*>(sm.misc);          // [TILE]
+    int* s_map = sm.misc + 64;                                        // [TILE] lane -> pool slot (>= TILE: after the flush)
+    int* s_ctl = sm.misc + 96;    // [0] pool fill, [1] configurations seen, [2] decided in phase A, [3] single-pass from now on
+    float* pool_q = reinterpret_cast<float*>(sm.ed);                  // [TILE][D]
+    if (threadIdx.x < 4) s_ctl[threadIdx.x] = 0;
+    __syncthreads();
+
+    // single-pass tile on the pooled survivors (n of them; idle lanes recompute slot 0)
+    auto run_pool = [&](int n) {
+        if (n < TILE) {
+            for (int i = threadIdx.x; i < (TILE - n) * D; i += THREADS) pool_q[n * D + i] = pool_q[i % D];
+            __syncthreads();
+        }
+        bool relpen;
+        const float total = process_tile<WARPS>(sm, pool_q, D, tol, true, false, &relpen);
+        if (warp == 0 && lane < n) p.flags[pool_idx[lane]] = total > tol ? 0 : 1;
+        __syncthreads();
+    };
+
     uint32_t phase[2] = {0, 0};
     int64_t tile = blockIdx.x;
     if (tile < n_tiles) fetch(tile, 0);
@@ -623,14 +738,64 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
         } else {
             __syncthreads();
         }
-        bool relpen = false;
-        const float total = process_tile<WARPS>(sm, sm.q[buf], D, tol, early, p.rule.enabled, &relpen);
-        if (warp == 0 && lane < nvalid) {
-            const bool coll = p.rule.enabled ? (total > tol && relpen) : (total > tol);
-            p.flags[first + lane] = coll ? 0 : 1;
-            if (p.pen_out) p.pen_out[first + lane] = total;
+        if (s_ctl[3]) {
+            bool relpen = false;
+            const float total = process_tile<WARPS>(sm, sm.q[buf], D, tol, true, false, &relpen);
+            if (warp == 0 && lane < nvalid) p.flags[first + lane] = total > tol ? 0 : 1;
+            __syncthreads();
+            continue;
+        }
+        // ---- phase A ----
+        const float bound_a = table_phase<WARPS>(sm, sm.q[buf], D);
+        if (warp == 0) {
+            int slot = -1;
+            const bool valid = lane < nvalid;
+            // the bound is exact arithmetic's lower bound; 4e-6 covers the fp32 rounding of both evaluations
+            const bool coll = bound_a - 4e-6f > tol;
+            if (valid && coll) p.flags[first + lane] = 0;
+            const unsigned surv = __ballot_sync(FULL, valid && !coll);
+            const int fill = s_ctl[0], room = TILE - fill;
+            if ((surv >> lane) & 1u) {
+                const int rank = __popc(surv & ((1u << lane) - 1u));
+                slot = rank < room ? fill + rank : TILE + rank - room;
+                if (slot < TILE) pool_idx[slot] = first + lane;
+            }
+            s_map[lane] = slot;
+            __syncwarp();
+            if (lane == 0) {
+                const int seen = s_ctl[1] + nvalid, decided = s_ctl[2] + nvalid - __popc(surv);
+                s_ctl[0] = fill + __popc(surv);   // > TILE: the pool is flushed once in between
+                s_ctl[1] = seen;
+                s_ctl[2] = decided;
+                if (seen >= 16 * TILE && decided * 4 < seen) s_ctl[3] = 1;   // phase A decides too little to pay for a second FK
+            }
         }
         __syncthreads();
+        for (int t = threadIdx.x; t < TILE * D; t += THREADS) {
+            const int c = t / D, sl = s_map[c];
+            if (sl >= 0 && sl < TILE) pool_q[sl * D + (t - c * D)] = sm.q[buf][t];
+        }
+        __syncthreads();
+        const int fill = s_ctl[0];
+        if (fill >= TILE) {
+            run_pool(TILE);
+            if (warp == 0) {
+                const int slot = s_map[lane];
+                if (slot >= TILE) pool_idx[slot - TILE] = first + lane;
+                if (lane == 0) s_ctl[0] = fill - TILE;
+            }
+            for (int t = threadIdx.x; t < TILE * D; t += THREADS) {
+                const int c = t / D, sl = s_map[c];
+                if (sl >= TILE) pool_q[(sl - TILE) * D + (t - c * D)] = sm.q[buf][t];
+            }
+        }
+        __syncthreads();
+    }
+    const int fill = s_ctl[0];
+    if (fill > 0) run_pool(fill);
+    if (p.stats && threadIdx.x == 0) {  // feedback for the launcher: how much phase A decides on this mode
+        atomicAdd(&p.stats[0], s_ctl[1]);
+        atomicAdd(&p.stats[1], s_ctl[2]);
     }
 }
 
@@ -865,23 +1030,29 @@ cudaError_t launch_static_penetration(uint32_t* blob, cudaStream_t st) {
 
 cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
-    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, false);
+    const bool two = p.two_phase && !p.full_eval && !p.rule.enabled && !p.pen_out;
+    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, two ? 2 : 0);
     const int64_t n_tiles = (p.B + TILE - 1) / TILE;
+#define MRB_LAUNCH_CONFIGS(W, T)                                              \
+    do {                                                                      \
+        int grid = grid_for(check_configs_kernel<W, T>, 32 * W, smem);        \
+        if (grid > n_tiles) grid = (int)n_tiles;                              \
+        check_configs_kernel<W, T><<<grid, 32 * W, smem, st>>>(p);            \
+    } while (0)
     if (warps_per_tile(p.world_words) == 4) {
-        int grid = grid_for(check_configs_kernel<4>, 128, smem);
-        if (grid > n_tiles) grid = (int)n_tiles;
-        check_configs_kernel<4><<<grid, 128, smem, st>>>(p);
+        if (two) MRB_LAUNCH_CONFIGS(4, true);
+        else MRB_LAUNCH_CONFIGS(4, false);
     } else {
-        int grid = grid_for(check_configs_kernel<2>, 64, smem);
-        if (grid > n_tiles) grid = (int)n_tiles;
-        check_configs_kernel<2><<<grid, 64, smem, st>>>(p);
+        if (two) MRB_LAUNCH_CONFIGS(2, true);
+        else MRB_LAUNCH_CONFIGS(2, false);
     }
+#undef MRB_LAUNCH_CONFIGS
     return cudaGetLastError();
 }
 
 cudaError_t launch_check_edges(const EdgeParams& p, cudaStream_t st) {
     if (p.E <= 0) return cudaSuccess;
-    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, true);
+    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, 1);
     cudaError_t err = cudaMemsetAsync(p.counter, 0, sizeof(int), st);
     if (err != cudaSuccess) return err;
     if (warps_per_tile(p.world_words) == 4) {

@@ -57,6 +57,7 @@ int main(int argc, char** argv) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     for (int i = 0; i < 3; i++) CK(mrb200_check_configs(scene, 0, dq, B, -1.f, dflags, nullptr, 0, nullptr));
+    cudaDeviceSynchronize();  // the library settles on a kernel variant once it has seen results of the first launches
     cudaEventRecord(e0);
     for (int i = 0; i < reps; i++) CK(mrb200_check_configs(scene, 0, dq, B, -1.f, dflags, nullptr, 0, nullptr));
     cudaEventRecord(e1);

@@ -282,3 +282,67 @@ def test_informed_batch_sampler_prunes_on_the_device(cuda_lib):
     q0, drawn0, pruned0 = model.sample_informed(slot, 10, np.stack([home, goal]), 0.5 * direct, "euclidean", "max",
                                                 np.random.RandomState(4), max_rounds=2)
     assert len(q0) == 0 and pruned0 == drawn0
+
+
+# ---- two-phase tiles (table / floor bound first, pooled survivors evaluated exactly) ----
+
+@pytest.mark.parametrize("name", ["box_rearrangement", "box_stacking", "mobile_wall_four"])
+@pytest.mark.parametrize("B", [4096, 4096 + 13, 50_001])
+def test_two_phase_tiles_give_the_single_pass_flags(be, name, B):
+    """Forced two-phase tiles, forced single pass and the full evaluation agree flag for flag (not only on the
+    margin-clear samples): survivors run through the same arithmetic, retired configurations are provably colliding."""
+    slot, sc, cs, kw = be.scenes[name]
+    q = torch.from_numpy(uniform_configs(sc, B, 31)).cuda()
+    try:
+        be.set_two_phase(slot, "never")
+        single = be.check_configs(slot, q).cpu().numpy()
+        be.set_two_phase(slot, "always")
+        two = be.check_configs(slot, q).cpu().numpy()
+    finally:
+        be.set_two_phase(slot, "auto")
+    assert np.array_equal(single, two), f"{(single != two).sum()} flags differ between the two kernels"
+    full = be.check_configs(slot, q, full_eval=True).cpu().numpy()
+    assert np.array_equal(full, two)
+    ofree, open_, omind = O.check_configs(cs.blob64, q.cpu().numpy().astype(np.float64), nthreads=O.max_threads())
+    clear = np.abs(O.margin(open_, omind, cs.tol)) > MARGIN
+    assert np.array_equal(two[clear], ofree[clear])
+
+
+def test_two_phase_on_inputs_the_bound_never_decides(be):
+    """All configurations at the (free) home pose: phase A retires nothing, every CTA falls back to single-pass
+    tiles, the pool is flushed, every flag is written exactly once."""
+    slot, sc, cs, kw = be.scenes["box_stacking"]
+    q = torch.from_numpy(np.tile(sc.home().astype(np.float32), (20_000 + 5, 1))).cuda()
+    try:
+        be.set_two_phase(slot, "always")
+        out = torch.full((q.shape[0],), 7, dtype=torch.uint8, device="cuda")
+        be.check_configs(slot, q, out=out)
+        assert bool((out == 1).all())
+        # and on inputs it always decides: every arm folded into the table
+        lim = sc.limits()
+        deep = uniform_configs(sc, 10_000, 5)
+        first = sc.robot_slices()[sc.robots[0]][0]
+        deep[:, first + 1] = 1.2   # robot 0: shoulder lift pointing down through the table
+        free = be.check_configs(slot, torch.from_numpy(deep).cuda()).cpu().numpy()
+        be.set_two_phase(slot, "never")
+        assert np.array_equal(free, be.check_configs(slot, torch.from_numpy(deep).cuda()).cpu().numpy())
+    finally:
+        be.set_two_phase(slot, "auto")
+
+
+def test_two_phase_policy_settles_from_measurements(be):
+    """auto: the first large batches measure how much the bound decides; the slot settles on two-phase tiles for
+    the four-arm scene (most uniform samples fold an arm into the table) and on single pass for the dual-arm one."""
+    for name, want in (("box_stacking", "two_phase"), ("box_rearrangement", "single_pass")):
+        slot, sc, cs, kw = be.scenes[name]
+        be.set_two_phase(slot, "auto")
+        assert be.two_phase_info(slot)["state"] == "measuring"
+        q = torch.from_numpy(uniform_configs(sc, 30_000, 8)).cuda()
+        a = be.check_configs(slot, q).cpu().numpy()     # measuring launch; .cpu() synchronises
+        b = be.check_configs(slot, q).cpu().numpy()     # reads the counters, settles
+        info = be.two_phase_info(slot)
+        assert info["state"] == want, info
+        assert info["seen"] >= 30_000 and 0 <= info["decided_by_bound"] <= info["seen"]
+        assert np.array_equal(a, b)
+        small = be.check_configs(slot, q[:100]).cpu().numpy()   # small batches never pool
+        assert np.array_equal(small, a[:100])
