@@ -434,14 +434,20 @@ struct Survivors {
 
 // One routine for every queued pair type: the broadphase only needs the records.
 template <int WARPS>
-__device__ __noinline__ void run_queued_types(const TileArgs args, int warp, bool skip_decided, unsigned tol_fx) {
+__device__ __noinline__ void run_queued_types(const TileArgs args, int warp, bool skip_decided, unsigned tol_fx, bool boxes_first) {
     const TileCtx c = make_ctx(args);
     const uint32_t* bi = c.bi;
     const float* bf = c.bf;
     const int lane = c.lane;
     const char* Wl = reinterpret_cast<const char*>(c.W + lane);  // this lane's column of W
     const float4* scentre = reinterpret_cast<const float4*>(bf + bi[MRB_H_OFF_SCENTRE]);
-    for (int type = 0; type <= MRB_PT_BOX_BOX; ++type) {
+    for (int ti = 0; ti <= MRB_PT_BOX_BOX; ++ti) {
+        // boxes_first: pairs against boxes (table, floor, objects) before the robot-robot types -- they decide most
+        // colliding configurations, and a decided configuration queues nothing for the types that follow
+        // (single-pass flag queries on uniform samples: +3.5 % dual-arm, +2 % mobile; the survivors of the two-phase
+        // tiles were NOT decided by the table, there the plain order is 2 % faster)
+        const int type = !boxes_first ? ti : ti < 3 ? (ti == 0 ? MRB_PT_SEG_BOX : ti == 1 ? MRB_PT_POINT_BOX : MRB_PT_BOX_BOX)
+                                                    : MRB_PT_BOX_BOX - ti;
         Survivors sv{c, args, type, 0};  // one queue per pair type: partial batches only at the end of a type
         for (int sub = 0; sub < MRB_BP_SUBLISTS; ++sub) {
             const int n = bi[MRB_H_BP + (type * MRB_BP_SUBLISTS + sub) * 2 + 1];
@@ -528,7 +534,7 @@ __device__ __forceinline__ void run_type_direct(const TileCtx& c, int warp) {
 // penetration (return value) and whether a relevant pair penetrates (*relpen_out).
 template <int WARPS>
 __device__ __forceinline__ float process_tile(const Smem& sm, const float* q_tile, int D, float tol, bool early, bool rule,
-                                              bool* relpen_out) {
+                                              bool* relpen_out, bool boxes_first = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t* bi = sm.blob;
     const float static_pen = reinterpret_cast<const float*>(bi)[MRB_H_STATIC_PEN];
@@ -547,7 +553,7 @@ __device__ __forceinline__ float process_tile(const Smem& sm, const float* q_til
     const TileArgs args{(uint32_t)((const unsigned char*)sm.blob - smem_raw), (uint32_t)((const unsigned char*)sm.W - smem_raw),
                         (uint32_t)((const unsigned char*)sm.sflag - smem_raw), (uint32_t)((const unsigned char*)sm.pen_fx - smem_raw),
                         (uint32_t)((const unsigned char*)(sm.queue + warp * QCAP) - smem_raw), rule};
-    run_queued_types<WARPS>(args, warp, early, tol_fx);
+    run_queued_types<WARPS>(args, warp, early, tol_fx, boxes_first);
     run_type_direct<MRB_PT_CYLZ_CYLZ, WARPS>(ctx, warp);
     run_type_direct<MRB_PT_BOX_CYLZ, WARPS>(ctx, warp);
     __syncthreads();
@@ -689,7 +695,7 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
                 __syncthreads();
             }
             bool relpen = false;
-            const float total = process_tile<WARPS>(sm, sm.q[buf], D, tol, early, p.rule.enabled, &relpen);
+            const float total = process_tile<WARPS>(sm, sm.q[buf], D, tol, early, p.rule.enabled, &relpen, early);
             if (warp == 0 && lane < nvalid) {
                 const bool coll = p.rule.enabled ? (total > tol && relpen) : (total > tol);
                 p.flags[first + lane] = coll ? 0 : 1;
@@ -937,6 +943,8 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(E
         }
         __syncthreads();
         bool relpen;
+        // full evaluation of every sample: stopping the decided samples early (as the configuration kernel does) gains
+        // 2-13 % on long uniform edges and loses 1-3 % on the short edges planners actually check (measured)
         const float total_pen = process_tile<WARPS>(sm, sm.q[0], D, tol, false, false, &relpen);
         if (warp == 0) {
             const unsigned hit = __ballot_sync(FULL, s_idx[lane] >= 0 && total_pen > tol);

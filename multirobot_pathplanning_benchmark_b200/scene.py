@@ -441,6 +441,7 @@ class CompiledScene:
     shape_names: List[str]
     pairs: List[Tuple[str, str]]
     tol: float
+    unreachable_pairs: List[Tuple[str, str]] = field(default_factory=list)  # collidable, but out of each other's reach
 
 
 def compile_blob(scene: Scene, tol: float) -> CompiledScene:
@@ -596,10 +597,56 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
         assert 0 <= shape_rows[i][2] * 128 < 65536, "world data of a configuration exceeds 64 KB"
         return shape_rows[i][2] * 128
 
+    # --- reach of every moving shape: a world-space ball that contains the centre of its bounding sphere for
+    # EVERY joint vector (hinge angles are not assumed to respect their limits: the queries are not validated
+    # against them either).  Walking up the chain, a hinge about axis a turns ball (c, r) into the ball around
+    # the axial part of c with radius r + |radial part of c|; a translating joint makes the reach unbounded.
+    # A pair whose reach balls, grown by the bounding radii, cannot meet never collides: it stays in the pair
+    # lists (the oracle evaluates it, the algorithmic flop count includes it) but gets no broadphase record.
+    HINGE_AXIS = {"hingeX": np.array([1.0, 0, 0]), "hingeY": np.array([0, 1.0, 0]), "hingeZ": np.array([0, 0, 1.0])}
+    code_joint = {v: k for k, v in JOINT_CODE.items()}
+    reach: List[Tuple[np.ndarray, float]] = []
+    for i in range(n_mov):
+        fid, L = shapes[i][0], shapes[i][5]
+        c, r = np.array(L.t, dtype=np.float64), 0.0
+        k = fid
+        while k >= 0:
+            par, jcode, _, A = frame_rows[k]
+            jt = code_joint[jcode]
+            if jt in HINGE_AXIS:
+                a = HINGE_AXIS[jt]
+                ax = a * float(a @ c)
+                r += float(np.linalg.norm(c - ax))
+                c = ax
+            else:
+                r = math.inf
+            c = np.asarray(A.apply(c), dtype=np.float64)
+            k = par
+        reach.append((c, r + bound_rs[i]))
+
+    def never_meets(x: int, y: int, kind: int) -> bool:
+        cx, rx_ = reach[x]
+        if not math.isfinite(rx_):
+            return False
+        if y < n_mov:
+            cy, ry_ = reach[y]
+            return math.isfinite(ry_) and float(np.linalg.norm(cx - cy)) > rx_ + ry_ + 2 * CULL_SLACK
+        core, _, _, rad_y, data, _ = shape_rows[y]
+        if core == CORE_BOX:  # distance from the reach centre to the static box itself (large tables)
+            ctr, R, half = np.array(data[:3]), np.array(data[3:12]).reshape(3, 3), np.array(data[12:15])
+            e = np.maximum(np.abs(R.T @ (cx - ctr)) - half, 0.0)
+            return float(np.linalg.norm(e)) > rx_ + rad_y + 2 * CULL_SLACK
+        ctr = 0.5 * (np.array(data[:3]) + np.array(data[3:6])) if core == CORE_SEG else np.array(data[:3])
+        return float(np.linalg.norm(cx - ctr)) > rx_ + bound_rs[y] + 2 * CULL_SLACK
+
     bp: List[List[List[Tuple[int, float, int]]]] = [[[] for _ in range(BP_SUBLISTS)] for _ in range(NUM_PAIR_TYPES)]
+    unreachable: List[Tuple[str, str]] = []
     for t in range(NUM_PAIR_TYPES):
         for (ia, ib, kind) in typed[t]:
             x, y = (ia, ib) if ia < n_mov else (ib, ia)   # X is always a moving shape
+            if t <= 5 and never_meets(x, y, kind):
+                unreachable.append((shapes[ia][1], shapes[ib][1]))
+                continue
             packed = ia | (ib << 16)
             rx, ry = shape_rows[x][3], shape_rows[y][3]
             if y < n_mov:
@@ -704,7 +751,7 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
         blob32=build(np.float32, np.int32, np.uint32), blob64=build(np.float64, np.int64, np.uint64), dof=scene.dof,
         n_frames=len(frame_rows), n_moving=n_mov, n_static=n_sta, world_words=world_words,
         pair_counts=[len(t) for t in typed], static_pair_count=len(static_pairs),
-        shape_names=[s[1] for s in shapes], pairs=all_pairs, tol=tol)
+        shape_names=[s[1] for s in shapes], pairs=all_pairs, tol=tol, unreachable_pairs=unreachable)
 
 
 # Algorithmic flop convention per pair type: used for roofline.achieved only.

@@ -1,0 +1,75 @@
+"""Reach analysis of the scene compiler (scene.py compile_blob): pairs that get no broadphase record because the
+two shapes can never meet.  Checked against the oracle's FK on joint vectors far outside the limits too -- the
+bound must hold for every hinge angle, queries are not validated against limits."""
+import numpy as np
+import pytest
+
+from multirobot_pathplanning_benchmark_b200 import scene as S
+from multirobot_pathplanning_benchmark_b200.scenes import SCENES
+from oracle import oracle_scene as O
+
+
+def _records(cs):
+    b = cs.blob64
+    out = set()
+    for t in range(6):
+        for k in range(S.BP_SUBLISTS):
+            off, n = int(b[S.H_BP + (t * S.BP_SUBLISTS + k) * 2]), int(b[S.H_BP + (t * S.BP_SUBLISTS + k) * 2 + 1])
+            for i in range(n):
+                pk = int(b[off + 2 * n + i])
+                out.add((pk & 0xffff, (pk >> 16) & 0xfff))
+    return out
+
+
+@pytest.mark.parametrize("name", ["box_rearrangement", "box_stacking"])
+def test_unreachable_pairs_never_come_close(name):
+    mk, kw = SCENES[name]
+    sc = mk()
+    cs = S.compile_blob(sc, kw["tol"])
+    assert len(cs.unreachable_pairs) > 0.05 * sum(cs.pair_counts)
+    idx = {n: i for i, n in enumerate(cs.shape_names)}
+    b = cs.blob64
+    ns = cs.n_moving + cs.n_static
+    offS = int(b[S.H_OFF_SHAPES])
+    rows = b[offS: offS + ns * S.SHAPE_WORDS].reshape(ns, S.SHAPE_WORDS)
+    core = rows[:, 0].astype(np.int64)
+    bound = rows[:, 19].view(np.float64)
+    rng = np.random.default_rng(0)
+    lim = sc.limits()
+    qs = np.concatenate([rng.uniform(lim[0], lim[1], (1500, sc.dof)), rng.uniform(-7.0, 7.0, (1500, sc.dof))])
+    closest = np.inf
+    for q in qs:
+        W = O.world_shapes(b, q, ns)
+        ctr = np.where((core == S.CORE_SEG)[:, None], 0.5 * (W[:, :3] + W[:, 3:6]), W[:, :3])
+        for a, c in cs.unreachable_pairs:
+            ia, ic = idx[a], idx[c]
+            if core[ic] == S.CORE_BOX and ic >= cs.n_moving:   # large static boxes: distance to the box itself
+                R, h = W[ic, 3:12].reshape(3, 3), W[ic, 12:15]
+                d = np.linalg.norm(np.maximum(np.abs(R.T @ (ctr[ia] - W[ic, :3])) - h, 0)) - bound[ia] - rows[ic, 3:4].view(np.float64)[0]
+            else:
+                d = np.linalg.norm(ctr[ia] - ctr[ic]) - bound[ia] - bound[ic]
+            closest = min(closest, d)
+    assert closest > S.CULL_SLACK, f"an 'unreachable' pair comes within {closest} of touching"
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_records_cover_every_reachable_pair(name):
+    mk, kw = SCENES[name]
+    cs = S.compile_blob(mk(), kw["tol"])
+    idx = {n: i for i, n in enumerate(cs.shape_names)}
+    recs = _records(cs)
+    skipped = {frozenset((idx[a], idx[c])) for a, c in cs.unreachable_pairs}
+    b = cs.blob64
+    n_queued = 0
+    for t in range(6):
+        n, off = int(b[S.H_N_PAIRS + t]), int(b[S.H_OFF_PAIRS + t])
+        for i in range(n):
+            pk = int(b[off + i])
+            a, c = pk & 0xffff, (pk >> 16) & 0xfff
+            if a >= cs.n_moving and c >= cs.n_moving:
+                continue
+            n_queued += 1
+            assert ((a, c) in recs) != (frozenset((a, c)) in skipped), "every dynamic pair is either recorded or proven unreachable"
+    assert n_queued == len(recs) + len(skipped)
+    if name in ("2d_handover", "mobile_wall_four"):   # translating bases reach everywhere
+        assert not skipped
