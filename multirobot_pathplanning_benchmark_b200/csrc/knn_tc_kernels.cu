@@ -33,6 +33,7 @@ constexpr int TC_STAGES = 3;      // shared-memory stages of corpus tiles
 constexpr int TC_THREADS = 384;   // warps 0-3: producer / MMA / TMEM allocator / spare, warps 4-11: epilogue
 constexpr int TC_STG = 8;         // staged candidates per epilogue thread between batched heap updates
 constexpr float TC_BIG = 1.0e30f;
+constexpr int TC_MAX_KS = 40;     // knn_tc_make_plan accepts plans up to this many K steps
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM primitives
@@ -187,6 +188,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
     uint64_t* tm_full = a_full + 1;             // [2] accumulators ready
     uint64_t* tm_empty = tm_full + 2;           // [2] accumulators drained by the epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
+    // issue table of the MMA thread, one entry per K step: A descriptor, B descriptor of stage 0, accumulator column
+    // offset | accumulate flag << 31.  Building descriptors inside the issue loop (address conversion, 64-bit shifts,
+    // plan look-ups) cost the single issuing thread more cycles per instruction than the tensor pipe needs to run it.
+    uint64_t* iss_a = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // [KS]
+    uint64_t* iss_b = iss_a + TC_MAX_KS;                              // [KS]
+    uint32_t* iss_d = reinterpret_cast<uint32_t*>(iss_b + TC_MAX_KS); // [KS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int buf_cols = n_acc * tn;            // TMEM columns per accumulator buffer
@@ -200,6 +207,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, alloc_cols);
+    if (warp == 1) {
+        for (int a = 0; a < n_acc; a++)
+            for (int ks = lane; ks < plan.ksteps[a]; ks += 32) {
+                const int kg = plan.kstep0[a] + ks;
+                iss_a[kg] = umma_desc(sA + (size_t)kg * TC_TM * 32);
+                iss_b[kg] = umma_desc(sB + (size_t)kg * tn * 32);
+                iss_d[kg] = (uint32_t)(a * tn) | (ks > 0 ? 0x80000000u : 0u);
+            }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -237,14 +253,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
                 mbar_wait(&tm_empty[buf], (use & 1) ^ 1);           // first use passes immediately
                 mbar_wait(&full_b[s], ph);
                 tc_fence_after();
-                const unsigned char* bs = sB + (size_t)s * b_bytes;
-                for (int a = 0; a < n_acc; a++) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * buf_cols + a * tn);
-                    for (int ks = 0; ks < plan.ksteps[a]; ks++) {
-                        const int kg = plan.kstep0[a] + ks;
-                        umma_tf32(d_tmem, umma_desc(sA + (size_t)kg * TC_TM * 32), umma_desc(bs + (size_t)kg * tn * 32), idesc,
-                                  ks > 0 ? 1u : 0u);
-                    }
+                const uint64_t stage_off = (uint64_t)(((uint32_t)s * b_bytes) >> 4);   // added to the 14-bit address field
+                const uint32_t d_base = tmem_base + (uint32_t)(buf * buf_cols);
+#pragma unroll 4
+                for (int kg = 0; kg < KS; kg++) {
+                    const uint32_t d = iss_d[kg];
+                    umma_tf32(d_base + (d & 0x7fffffffu), iss_a[kg], iss_b[kg] + stage_off, idesc, d >> 31);
                 }
                 umma_commit(&empty_b[s]);     // the stage may be refilled once these MMAs have read it
                 umma_commit(&tm_full[buf]);   // accumulators complete
@@ -449,11 +463,11 @@ bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan) {
     }
     int tn = 256 / plan->n_acc;
     plan->tn = tn >= 256 ? 256 : tn >= 128 ? 128 : tn >= 64 ? 64 : 32;
-    return plan->KS <= 40;
+    return plan->KS <= TC_MAX_KS;
 }
 
 size_t knn_tc_smem_bytes(const TcPlan& plan, int kc) {
-    return (size_t)plan.KS * TC_TM * 32 + (size_t)TC_STAGES * plan.KS * plan.tn * 32 + (size_t)(kc + TC_STG) * 2 * TC_TM * 8 + 16 * 8 + 1024;
+    return (size_t)plan.KS * TC_TM * 32 + (size_t)TC_STAGES * plan.KS * plan.tn * 32 + (size_t)(kc + TC_STG) * 2 * TC_TM * 8 + 16 * 8 + (size_t)TC_MAX_KS * 20 + 1024;
 }
 
 int knn_tc_splits(int64_t Q, int64_t n_ctiles) {

@@ -777,9 +777,10 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
             }
         }
         __syncthreads();
-        for (int t = threadIdx.x; t < TILE * D; t += THREADS) {
-            const int c = t / D, sl = s_map[c];
-            if (sl >= 0 && sl < TILE) pool_q[sl * D + (t - c * D)] = sm.q[buf][t];
+        for (int c = warp; c < TILE; c += WARPS) {  // a warp per surviving row (no division by D)
+            const int sl = s_map[c];
+            if (sl >= 0 && sl < TILE)
+                for (int k = lane; k < D; k += 32) pool_q[sl * D + k] = sm.q[buf][c * D + k];
         }
         __syncthreads();
         const int fill = s_ctl[0];
@@ -790,9 +791,10 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
                 if (slot >= TILE) pool_idx[slot - TILE] = first + lane;
                 if (lane == 0) s_ctl[0] = fill - TILE;
             }
-            for (int t = threadIdx.x; t < TILE * D; t += THREADS) {
-                const int c = t / D, sl = s_map[c];
-                if (sl >= TILE) pool_q[(sl - TILE) * D + (t - c * D)] = sm.q[buf][t];
+            for (int c = warp; c < TILE; c += WARPS) {
+                const int sl = s_map[c];
+                if (sl >= TILE)
+                    for (int k = lane; k < D; k += 32) pool_q[(sl - TILE) * D + k] = sm.q[buf][c * D + k];
             }
         }
         __syncthreads();
