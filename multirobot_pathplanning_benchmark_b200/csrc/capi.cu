@@ -358,13 +358,18 @@ static int check_configs_impl(const mrb200_scene_t* sc, int slot, const float* q
     const bool eligible = s->n_large > 0 && B >= 4096 && !pen_dev && !full_eval && !rule.enabled;
     bool measuring = false;
     if (eligible && forced < 0) {
-        if (s->two_phase_state == 0 && !s->two_phase_forced) {
+        // (several host threads may query one handle: the state is a relaxed atomic; a lost race only repeats the decision)
+        int state = __atomic_load_n(&s->two_phase_state, __ATOMIC_RELAXED);
+        if (state == 0 && !s->two_phase_forced) {
             const volatile int* st2 = sc->stats_pin + 2 * slot;
             const int seen = st2[0], decided = st2[1];
-            if (seen >= 4096) s->two_phase_state = (int64_t)decided * 20 >= (int64_t)seen * 11 ? 1 : 2;
+            if (seen >= 4096) {
+                state = (int64_t)decided * 20 >= (int64_t)seen * 11 ? 1 : 2;
+                __atomic_store_n(&s->two_phase_state, state, __ATOMIC_RELAXED);
+            }
         }
-        p.two_phase = s->two_phase_state != 2;
-        measuring = s->two_phase_state == 0 && !s->two_phase_forced;
+        p.two_phase = state != 2;
+        measuring = state == 0 && !s->two_phase_forced;
     } else {
         p.two_phase = eligible && forced == 1;
     }

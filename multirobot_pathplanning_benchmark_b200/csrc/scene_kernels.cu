@@ -645,6 +645,16 @@ __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob
     __syncthreads();
 }
 
+// One complete single-pass tile as an out-of-line call (two-phase kernel only: pooled survivors, the final flush and
+// the single-pass fallback share ONE copy of FK + pair code instead of three inlined ones; the shared-memory
+// pointers are rebuilt from the layout parameters so that they stay shared-space pointers, see TileArgs).
+template <int WARPS>
+__device__ __noinline__ float full_tile_call(int blob_words, int D, int world_words, int n_shapes, uint32_t q_off, float tol) {
+    const Smem sm = carve(smem_raw, blob_words, D, world_words, n_shapes, 2);
+    bool relpen;
+    return process_tile<WARPS>(sm, reinterpret_cast<const float*>(smem_raw + q_off), D, tol, true, false, &relpen);
+}
+
 // ------------------------------------------------------------------------------------------
 // configuration batch kernel (A5 / A6 batch variant)
 // ------------------------------------------------------------------------------------------
@@ -723,8 +733,8 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
             for (int i = threadIdx.x; i < (TILE - n) * D; i += THREADS) pool_q[n * D + i] = pool_q[i % D];
             __syncthreads();
         }
-        bool relpen;
-        const float total = process_tile<WARPS>(sm, pool_q, D, tol, true, false, &relpen);
+        const float total = full_tile_call<WARPS>(p.blob_words, D, p.world_words, p.n_shapes,
+                                                  (uint32_t)((const unsigned char*)pool_q - smem_raw), tol);
         if (warp == 0 && lane < n) p.flags[pool_idx[lane]] = total > tol ? 0 : 1;
         __syncthreads();
     };
@@ -745,8 +755,8 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
             __syncthreads();
         }
         if (s_ctl[3]) {
-            bool relpen = false;
-            const float total = process_tile<WARPS>(sm, sm.q[buf], D, tol, true, false, &relpen);
+            const float total = full_tile_call<WARPS>(p.blob_words, D, p.world_words, p.n_shapes,
+                                                      (uint32_t)((const unsigned char*)sm.q[buf] - smem_raw), tol);
             if (warp == 0 && lane < nvalid) p.flags[first + lane] = total > tol ? 0 : 1;
             __syncthreads();
             continue;
@@ -777,10 +787,9 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
             }
         }
         __syncthreads();
-        for (int c = warp; c < TILE; c += WARPS) {  // a warp per surviving row (no division by D)
-            const int sl = s_map[c];
-            if (sl >= 0 && sl < TILE)
-                for (int k = lane; k < D; k += 32) pool_q[sl * D + k] = sm.q[buf][c * D + k];
+        for (int t = threadIdx.x; t < TILE * D; t += THREADS) {
+            const int c = t / D, sl = s_map[c];
+            if (sl >= 0 && sl < TILE) pool_q[sl * D + (t - c * D)] = sm.q[buf][t];
         }
         __syncthreads();
         const int fill = s_ctl[0];
@@ -791,10 +800,9 @@ __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel
                 if (slot >= TILE) pool_idx[slot - TILE] = first + lane;
                 if (lane == 0) s_ctl[0] = fill - TILE;
             }
-            for (int c = warp; c < TILE; c += WARPS) {
-                const int sl = s_map[c];
-                if (sl >= TILE)
-                    for (int k = lane; k < D; k += 32) pool_q[(sl - TILE) * D + k] = sm.q[buf][c * D + k];
+            for (int t = threadIdx.x; t < TILE * D; t += THREADS) {
+                const int c = t / D, sl = s_map[c];
+                if (sl >= TILE) pool_q[(sl - TILE) * D + (t - c * D)] = sm.q[buf][t];
             }
         }
         __syncthreads();

@@ -36,6 +36,10 @@ def test_pure_argument_checks_need_no_device(cuda_lib):
     assert cuda_lib.mrb200_check_configs(None, 0, None, 10, -1.0, None, None, 0, None) == ERR_ARG
     assert cuda_lib.mrb200_scene_destroy(None) == 0 and cuda_lib.mrb200_abstract_destroy(None) == 0
     assert cuda_lib.mrb200_version() >= 1
+    out3 = (C.c_int32 * 3)()
+    assert cuda_lib.mrb200_scene_set_two_phase(None, 0, 1) == ERR_ARG
+    assert cuda_lib.mrb200_scene_get_two_phase(None, 0, out3) == ERR_ARG
+    assert b"two_phase" in cuda_lib.mrb200_last_error()
 
 
 @pytest.mark.gpu
