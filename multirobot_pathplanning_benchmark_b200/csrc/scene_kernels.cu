@@ -658,8 +658,11 @@ __device__ __noinline__ float full_tile_call(int blob_words, int D, int world_wo
 // ------------------------------------------------------------------------------------------
 // configuration batch kernel (A5 / A6 batch variant)
 // ------------------------------------------------------------------------------------------
-template <int WARPS, bool TWO_PHASE>
-__global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_configs_kernel(ConfigParams p) {
+// MINB: CTAs per SM the register allocation has to allow.  16 resident warps by default; scenes whose shared-memory
+// footprint admits only three 4-warp CTAs anyway (four-arm scene: 65 KB) get the variant compiled for three, i.e. up
+// to 168 registers per thread instead of 128.
+template <int WARPS, bool TWO_PHASE, int MINB = 16 / WARPS>
+__global__ void __launch_bounds__(TILE * WARPS, MINB) check_configs_kernel(ConfigParams p) {
     constexpr int THREADS = TILE * WARPS;
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, TWO_PHASE ? 2 : 0);
     stage_scene(sm, p.blob, p.blob_words, p.n_shapes, p.rule, THREADS);
@@ -1051,14 +1054,17 @@ cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st) {
     const bool two = p.two_phase && !p.full_eval && !p.rule.enabled && !p.pen_out;
     const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, two ? 2 : 0);
     const int64_t n_tiles = (p.B + TILE - 1) / TILE;
-#define MRB_LAUNCH_CONFIGS(W, T)                                              \
-    do {                                                                      \
-        int grid = grid_for(check_configs_kernel<W, T>, 32 * W, smem);        \
-        if (grid > n_tiles) grid = (int)n_tiles;                              \
-        check_configs_kernel<W, T><<<grid, 32 * W, smem, st>>>(p);            \
+#define MRB_LAUNCH_CONFIGS(W, ...)                                                      \
+    do {                                                                                \
+        int grid = grid_for(check_configs_kernel<W, __VA_ARGS__>, 32 * W, smem);        \
+        if (grid > n_tiles) grid = (int)n_tiles;                                        \
+        check_configs_kernel<W, __VA_ARGS__><<<grid, 32 * W, smem, st>>>(p);            \
     } while (0)
     if (warps_per_tile(p.world_words) == 4) {
-        if (two) MRB_LAUNCH_CONFIGS(4, true);
+        const bool three = 4 * (smem + 1024) > 228 * 1024;   // shared memory admits three CTAs per SM at most
+        if (two && three) MRB_LAUNCH_CONFIGS(4, true, 3);
+        else if (two) MRB_LAUNCH_CONFIGS(4, true);
+        else if (three) MRB_LAUNCH_CONFIGS(4, false, 3);
         else MRB_LAUNCH_CONFIGS(4, false);
     } else {
         if (two) MRB_LAUNCH_CONFIGS(2, true);
