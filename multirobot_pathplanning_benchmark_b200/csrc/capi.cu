@@ -35,7 +35,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 struct ModeSlot {
     uint32_t* blob = nullptr;  // device
-    int words = 0, D = 0, world_words = 0, n_shapes = 0, n_pairs = 0;
+    int words = 0, staged = 0, D = 0, world_words = 0, n_shapes = 0, n_pairs = 0;   // staged: prefix kept in shared memory
     int n_large = 0;           // pairs against large static boxes (table, floor): phase A of the two-phase tiles
     // two-phase tiles pay off when phase A decides most configurations; that depends on the caller's inputs, so the
     // first large batches measure it (device counters copied to pinned memory behind the launch, read without
@@ -253,6 +253,9 @@ int mrb200_scene_set_mode(mrb200_scene_t* sc, int slot, const void* blob_host, s
     if (nbytes < MRB_HDR_WORDS * 4 || h[MRB_H_MAGIC] != MRB_BLOB_MAGIC || h[MRB_H_VERSION] != MRB_BLOB_VERSION ||
         (size_t)h[MRB_H_TOTAL_WORDS] * 4 != nbytes || (nbytes & 15))
         return fail(MRB200_ERR_BLOB, "scene_set_mode: not a version-%d scene blob of %zu bytes", MRB_BLOB_VERSION, nbytes);
+    if (h[MRB_H_STAGED_WORDS] < MRB_HDR_WORDS || h[MRB_H_STAGED_WORDS] > h[MRB_H_TOTAL_WORDS] || (h[MRB_H_STAGED_WORDS] & 3) ||
+        h[MRB_H_REC_BASE] > h[MRB_H_STAGED_WORDS] || h[MRB_H_IDS_BASE] < h[MRB_H_REC_BASE] || h[MRB_H_IDS_BASE] > h[MRB_H_TOTAL_WORDS])
+        return fail(MRB200_ERR_BLOB, "scene_set_mode: inconsistent staged / tail split in the blob header");
     const int n_shapes = (int)(h[MRB_H_NMOV] + h[MRB_H_NSTA]);
     if (n_shapes > 256) return fail(MRB200_ERR_ARG, "scene_set_mode: more than 256 collision shapes");
     ModeSlot& s = sc->slots[slot];
@@ -270,6 +273,7 @@ int mrb200_scene_set_mode(mrb200_scene_t* sc, int slot, const void* blob_host, s
     e = cudaStreamSynchronize(st);  // blob_host may be pageable and freed by the caller
     if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: sync");
     s.words = (int)h[MRB_H_TOTAL_WORDS];
+    s.staged = (int)h[MRB_H_STAGED_WORDS];
     s.D = (int)h[MRB_H_DOF];
     s.world_words = (int)h[MRB_H_WORLD_WORDS];
     s.n_shapes = n_shapes;
@@ -282,8 +286,8 @@ int mrb200_scene_set_mode(mrb200_scene_t* sc, int slot, const void* blob_host, s
     sc->stats_pin[2 * slot] = sc->stats_pin[2 * slot + 1] = 0;
     e = cudaMemsetAsync(sc->stats_dev + 2 * slot, 0, 2 * sizeof(int), st);
     if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: counters");
-    if (mrb::scene_smem_bytes(s.words, s.D, s.world_words, s.n_shapes, 1) > 227 * 1024 ||
-        mrb::scene_smem_bytes(s.words, s.D, s.world_words, s.n_shapes, 2) > 227 * 1024)
+    if (mrb::scene_smem_bytes(s.staged, s.D, s.world_words, s.n_shapes, 1) > 227 * 1024 ||
+        mrb::scene_smem_bytes(s.staged, s.D, s.world_words, s.n_shapes, 2) > 227 * 1024)
         return fail(MRB200_ERR_ARG, "scene_set_mode: scene needs more than 227 KB of shared memory per CTA");
     e = mrb::launch_static_penetration(s.blob, st);
     if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: static pairs");
@@ -302,7 +306,7 @@ int mrb200_scene_info(const mrb200_scene_t* sc, int slot, int32_t* out4) {
     out4[0] = s->D;
     out4[1] = s->n_shapes;
     out4[2] = s->n_pairs;
-    out4[3] = (int32_t)mrb::scene_smem_bytes(s->words, s->D, s->world_words, s->n_shapes);
+    out4[3] = (int32_t)mrb::scene_smem_bytes(s->staged, s->D, s->world_words, s->n_shapes);
     return MRB200_OK;
 }
 
@@ -340,7 +344,7 @@ static int check_configs_impl(const mrb200_scene_t* sc, int slot, const float* q
     if (B == 0) return MRB200_OK;
     mrb::ConfigParams p{};
     p.blob = s->blob;
-    p.blob_words = s->words;
+    p.blob_words = s->staged;
     p.D = s->D;
     p.world_words = s->world_words;
     p.n_shapes = s->n_shapes;
@@ -415,7 +419,7 @@ int mrb200_check_edges(const mrb200_scene_t* sc, int slot, const float* q1, cons
     if (E == 0) return MRB200_OK;
     mrb::EdgeParams p{};
     p.blob = s->blob;
-    p.blob_words = s->words;
+    p.blob_words = s->staged;
     p.D = s->D;
     p.world_words = s->world_words;
     p.n_shapes = s->n_shapes;

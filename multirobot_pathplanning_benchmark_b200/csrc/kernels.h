@@ -14,8 +14,9 @@ struct RobotRule {
 };
 
 struct ConfigParams {
-    const uint32_t* blob;  // device, compiled scene for the mode
-    int blob_words, D, world_words, n_shapes;
+    const uint32_t* blob;  // device, compiled scene for the mode (all of it)
+    int blob_words;        // MRB_H_STAGED_WORDS: the prefix the kernel stages in shared memory
+    int D, world_words, n_shapes;
     const float* q;  // device [B, D]
     int64_t B;
     float tol;        // < 0: use the blob's

@@ -19,8 +19,8 @@
 #define MRB_SCENE_BLOB_H
 
 #define MRB_BLOB_MAGIC 0x4D524232
-#define MRB_BLOB_VERSION 6
-#define MRB_HDR_WORDS 112
+#define MRB_BLOB_VERSION 7
+#define MRB_HDR_WORDS 136
 #define MRB_FRAME_WORDS 16
 #define MRB_SHAPE_WORDS 20
 #define MRB_NUM_PAIR_TYPES 8
@@ -67,19 +67,26 @@
 #define MRB_H_STATIC_PEN 14 /* float: filled on the device by mrb200_scene_set_mode */
 #define MRB_H_TOTAL_WORDS 15
 #define MRB_H_NROBOTS 16
+#define MRB_H_STAGED_WORDS 17 /* prefix the kernels copy into shared memory; the rest is read from global memory */
+#define MRB_H_REC_BASE 18     /* first word of the broadphase records (staged) */
+#define MRB_H_IDS_BASE 19     /* first word of the records' packed pair ids, one per record, in record order; inside the \
+                                 staged prefix on small scenes, in the tail on large ones */
 #define MRB_H_OFF_PAIRS 20 /* [20..27] */
 #define MRB_H_N_PAIRS 28   /* [28..35] */
 #define MRB_H_OFF_SHAPE_ROBOT 36
 #define MRB_H_OFF_SCENTRE 37 /* static shape centres, 4 floats each */
+#define MRB_H_IDS_STAGED 38  /* 1: the records' pair ids are part of the staged prefix */
+#define MRB_H_GPTR 40        /* [40..41] device only: each CTA parks the blob's global address here after staging */
 /* broadphase sublists [type][sublist] -> (record offset, count).  A record is 2 words
- * { (byte offset of moving shape X inside a W row) | (Y id << 16), float threshold }; the n records
- * of a sublist are followed by n packed (a | b << 16) pair ids for the narrowphase.
+ * { (byte offset of moving shape X inside a W row) | (Y id << 16), float threshold }; record r (counted from
+ * MRB_H_REC_BASE) has its packed (a | b << 16) pair ids for the narrowphase at word MRB_H_IDS_BASE + r.
  *   sublist 0: Y moving (id = its byte offset), bounding spheres, threshold = (bX + bY + slack)^2
  *   sublist 1: Y static (id = static index),    bounding spheres, same threshold
  *   sublist 2: Y a large static box (id = static index), separating-axis bound along the box's
  *              face normals; threshold = rX + rY + slack (X a segment) or bX + rY + slack */
 #define MRB_H_BP 48
 #define MRB_BP_SUBLISTS 3
+#define MRB_H_BP_IDS 112 /* [type][sublist] -> first word of the sublist's packed pair ids (= MRB_H_IDS_BASE + record number) */
 
 /* threshold below which a box-box edge-edge SAT axis (|a_i x b_j|^2) is skipped as degenerate */
 #define MRB_SAT_PARALLEL_EPS2 1e-4

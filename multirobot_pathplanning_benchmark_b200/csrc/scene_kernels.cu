@@ -39,8 +39,10 @@ constexpr unsigned FULL = 0xffffffffu;
 // derived from this symbol is known to be shared (LDS / STS / ATOMS, 32-bit addresses).
 extern __shared__ __align__(128) unsigned char smem_raw[];
 
+// (shared-memory pointers only: a global pointer stored next to them makes nvcc address the whole struct's
+// pointers through global stores -- STG.E to a shared-window address faults)
 struct Smem {
-    uint32_t* blob;  // staged scene blob
+    uint32_t* blob;  // staged prefix of the scene blob
     float* q[2];     // configuration tiles [TILE][D]
     float* W;        // world shape data [world_words][TILE]
     unsigned* pen_fx;  // [TILE] fixed-point penetration per configuration
@@ -373,9 +375,14 @@ __device__ __noinline__ void drain(const TileArgs args, uint32_t entry, bool val
     if (valid) {
         const TileCtx c = make_ctx(args);
         const int cfg = entry & 31;
-        const int hdr = MRB_H_BP + (T * MRB_BP_SUBLISTS + (int)(entry >> 29)) * 2;
-        // a sublist's n records (2 words each) are followed by its n packed pair ids
-        const uint32_t pk = c.bi[c.bi[hdr] + 2 * c.bi[hdr + 1] + ((entry >> 5) & 0xffffffu)];
+        // record r of the blob has its packed pair ids at ids[r] (blob tail, global memory)
+        // the pair ids of the entry's record: staged with the blob prefix on small scenes, else read from the blob's
+        // tail in global memory (its address is parked in the staged header; keeping the pointer in TileArgs instead
+        // costs two registers across the broadphase loops and 1-2 % on the small scenes)
+        const uint32_t w = c.bi[MRB_H_BP_IDS + T * MRB_BP_SUBLISTS + (int)(entry >> 29)] + ((entry >> 5) & 0xffffffu);
+        uint32_t pk;
+        if (c.bi[MRB_H_IDS_STAGED]) pk = c.bi[w];   // warp-uniform
+        else pk = (*reinterpret_cast<const uint32_t* const*>(c.bi + MRB_H_GPTR))[w];
         const int a = pk & 0xffff, b = (pk >> 16) & 0xfff;
         c.add_pen(cfg, a, b, narrow_pair<T>(c, a, b, cfg));
     }
@@ -589,8 +596,15 @@ __device__ __forceinline__ float table_phase(const Smem& sm, const float* q_tile
         const uint2* rec = reinterpret_cast<const uint2*>(bi + off);
         const int lo = (n * warp) / WARPS, hi = (n * (warp + 1)) / WARPS;
         for (int i = lo; i < hi; ++i) {
-            const uint32_t rx = rec[i].x, pk = bi[off + 2 * n + i];
-            const float rsum = bf[offS + (int)(pk & 0xffff) * MRB_SHAPE_WORDS + 3] + bf[offS + (int)((pk >> 16) & 0xfff) * MRB_SHAPE_WORDS + 3];
+            const uint2 rc = rec[i];
+            const uint32_t rx = rc.x;
+            // r_X + r_Y: the record's threshold minus the cull slack for points and segments; a moving box's threshold
+            // is built from its bounding radius, so its radii come from the pair ids in the blob tail
+            float rsum = __uint_as_float(rc.y) - CULL_SLACK;
+            if (type == MRB_PT_BOX_BOX) {
+                const uint32_t pk = (*reinterpret_cast<const uint32_t* const*>(bi + MRB_H_GPTR))[bi[MRB_H_IDS_BASE] + ((off - (int)bi[MRB_H_REC_BASE]) >> 1) + i];
+                rsum = bf[offS + (int)(pk & 0xffff) * MRB_SHAPE_WORDS + 3] + bf[offS + (int)((pk >> 16) & 0xfff) * MRB_SHAPE_WORDS + 3];
+            }
             const float* px = reinterpret_cast<const float*>(Wl + (rx & 0xffffu));
             const float* B = bf + offS + (nmov + (int)(rx >> 16)) * MRB_SHAPE_WORDS + 4;  // c[3], R[9], half[3]
             const float* R = B + 3;
@@ -642,6 +656,7 @@ __device__ __forceinline__ void stage_scene(const Smem& sm, const uint32_t* blob
         sm.sflag[s] = (uint8_t)f;
     }
     mbar_wait(&sm.bar[0], 0);
+    if (threadIdx.x == 0) *reinterpret_cast<const uint32_t**>(sm.blob + MRB_H_GPTR) = blob;  // for readers of the blob's tail
     __syncthreads();
 }
 

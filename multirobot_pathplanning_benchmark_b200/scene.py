@@ -402,8 +402,8 @@ class Scene:
 # blob layout (mirror of csrc/scene_blob.h)
 # ----------------------------------------------------------------------------------
 BLOB_MAGIC = 0x4D524232
-BLOB_VERSION = 6
-HDR_WORDS = 112
+BLOB_VERSION = 7
+HDR_WORDS = 136
 FRAME_WORDS = 16
 SHAPE_WORDS = 20
 LARGE_BOX_BOUND = 0.3  # boxes with a bounding radius above this use the face-normal broadphase bound
@@ -415,6 +415,12 @@ WORLD_WORDS = {CORE_POINT: 3, CORE_SEG: 6, CORE_BOX: 12, CORE_CYLZ: 3}
 H_MAGIC, H_VERSION, H_DOF, H_NFRAMES, H_NMOV, H_NSTA, H_WORLD_WORDS, H_NCHAINS = range(8)
 H_OFF_FRAMES, H_OFF_SHAPES, H_OFF_CHAINS, H_OFF_STATIC_PAIRS, H_N_STATIC_PAIRS = 8, 9, 10, 11, 12
 H_TOL, H_STATIC_PEN, H_TOTAL_WORDS, H_NROBOTS = 13, 14, 15, 16
+H_STAGED_WORDS = 17  # the kernels copy only this prefix into shared memory; the tail is read from global memory
+H_REC_BASE = 18      # first word of the broadphase records
+H_IDS_BASE = 19      # first word of the packed pair ids, one per record, in record order
+H_IDS_STAGED = 38    # 1: the pair ids are part of the staged prefix
+H_GPTR = 40          # [40..41] device only: the kernels park the blob's global address here after staging
+H_BP_IDS = 112       # [type][sublist] -> first word of the sublist's pair ids (8 x 3 words)
 H_OFF_PAIRS = 20   # [20..27]
 H_N_PAIRS = 28     # [28..35]
 H_OFF_SHAPE_ROBOT = 36
@@ -422,6 +428,7 @@ H_OFF_SCENTRE = 37   # static shape centres, 4 floats each
 H_BP = 48            # broadphase sublists: [type][sublist] -> (record offset, count), 8 x 3 x 2 words
 BP_SUBLISTS = 3      # 0: partner moving (bounding spheres), 1: partner static (bounding spheres),
                      # 2: partner is a large static box (face-normal separating-axis bound)
+STAGE_IDS_MAX_BYTES = 12 * 1024   # blobs whose staged prefix stays below this keep the records' pair ids in it
 CULL_SLACK = 1e-3    # broadphase keeps everything closer than 1 mm  # per-shape robot id (moving shapes: owning robot; static: -1; held: holder)
 
 
@@ -432,6 +439,7 @@ class CompiledScene:
     blob32: np.ndarray            # uint32
     blob64: np.ndarray            # uint64 (ints stored as uint64, floats as float64 bits)
     dof: int
+    staged_words: int             # prefix of the blob the kernels keep in shared memory
     n_frames: int
     n_moving: int
     n_static: int
@@ -660,7 +668,12 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
             sl.sort(key=lambda r: (r[0] & 0xffff, r[0] >> 16))
 
     # --- assemble words ---
+    # staged prefix (copied into shared memory by every CTA): header, frames, shapes, chains, the pair lists of the
+    # directly evaluated planar types, static shape centres, broadphase records.  Tail (global memory only): the pair
+    # lists of the queued types (the kernels work from the records; the oracle and the host read these), static-static
+    # pairs, per-shape robot ids, and the records' packed pair ids (one read per narrowphase item).
     n_shapes = len(shapes)
+    DIRECT_TYPES = (6, 7)
     off = HDR_WORDS
     off_frames = off
     off += FRAME_WORDS * len(frame_rows)
@@ -668,24 +681,41 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
     off += SHAPE_WORDS * n_shapes
     off_chains = off
     off += 2 * len(chain_rows)
-    off_pairs = []
-    for t in range(NUM_PAIR_TYPES):
-        off_pairs.append(off)
+    off_pairs = [0] * NUM_PAIR_TYPES
+    for t in DIRECT_TYPES:
+        off_pairs[t] = off
         off += len(typed[t])
+    off = (off + 3) // 4 * 4
+    off_scentre = off
+    off += 4 * n_sta
+    off = (off + 1) // 2 * 2              # records are read as 8-byte words
+    rec_base = off
+    off_bp = [[0] * BP_SUBLISTS for _ in range(NUM_PAIR_TYPES)]
+    for t in range(NUM_PAIR_TYPES):
+        for k in range(BP_SUBLISTS):
+            off_bp[t][k] = off
+            off += 2 * len(bp[t][k])
+    n_records = (off - rec_base) // 2
+    # small scenes keep the pair ids in the staged prefix too (one shared-memory read per narrowphase item instead of
+    # a global one: 1.3 % on the dual-arm scene); on large scenes they are what lets a fourth CTA fit on an SM
+    ids_staged = (off + n_records) * 4 <= STAGE_IDS_MAX_BYTES
+    ids_base = off
+    if ids_staged:
+        off += n_records
+    staged = (off + 3) // 4 * 4           # 16-byte multiple for cp.async.bulk
+    off = staged
+    for t in range(NUM_PAIR_TYPES):
+        if t not in DIRECT_TYPES:
+            off_pairs[t] = off
+            off += len(typed[t])
     off_static = off
     off += 3 * len(static_pairs)
     off_shape_robot = off
     off += n_shapes
-    off = (off + 3) // 4 * 4
-    off_scentre = off
-    off += 4 * n_sta
-    off_bp = [[0] * BP_SUBLISTS for _ in range(NUM_PAIR_TYPES)]
-    for t in range(NUM_PAIR_TYPES):
-        for k in range(BP_SUBLISTS):
-            off = (off + 1) // 2 * 2          # records are read as 8-byte words
-            off_bp[t][k] = off
-            off += 3 * len(bp[t][k])          # n records (2 words) then n packed pair ids
-    total = (off + 3) // 4 * 4   # 16-byte multiple for cp.async.bulk
+    if not ids_staged:
+        ids_base = off
+        off += n_records
+    total = (off + 3) // 4 * 4
 
     ints = np.zeros(total, np.int64)
     flts = np.zeros(total, np.float64)
@@ -705,6 +735,7 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
     seti(H_OFF_STATIC_PAIRS, off_static), seti(H_N_STATIC_PAIRS, len(static_pairs))
     setf(H_TOL, tol), setf(H_STATIC_PEN, 0.0), seti(H_TOTAL_WORDS, total)
     seti(H_NROBOTS, len(scene.robots)), seti(H_OFF_SHAPE_ROBOT, off_shape_robot)
+    seti(H_STAGED_WORDS, staged), seti(H_REC_BASE, rec_base), seti(H_IDS_BASE, ids_base), seti(H_IDS_STAGED, int(ids_staged))
     for t in range(NUM_PAIR_TYPES):
         seti(H_OFF_PAIRS + t, off_pairs[t]), seti(H_N_PAIRS + t, len(typed[t]))
     for i, (par, jt, qi, A) in enumerate(frame_rows):
@@ -736,9 +767,10 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
         for k in range(BP_SUBLISTS):
             n = len(bp[t][k])
             seti(H_BP + (t * BP_SUBLISTS + k) * 2, off_bp[t][k]), seti(H_BP + (t * BP_SUBLISTS + k) * 2 + 1, n)
+            seti(H_BP_IDS + t * BP_SUBLISTS + k, ids_base + (off_bp[t][k] - rec_base) // 2)
             for i, (ids, thr, packed) in enumerate(bp[t][k]):
                 seti(off_bp[t][k] + 2 * i, ids), setf(off_bp[t][k] + 2 * i + 1, thr)
-                seti(off_bp[t][k] + 2 * n + i, packed)
+                seti(ids_base + (off_bp[t][k] - rec_base) // 2 + i, packed)
     for i, (t, a, b_) in enumerate(static_pairs):
         seti(off_static + 3 * i, t), seti(off_static + 3 * i + 1, a), seti(off_static + 3 * i + 2, b_)
 
@@ -749,6 +781,7 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
 
     return CompiledScene(
         blob32=build(np.float32, np.int32, np.uint32), blob64=build(np.float64, np.int64, np.uint64), dof=scene.dof,
+        staged_words=staged,
         n_frames=len(frame_rows), n_moving=n_mov, n_static=n_sta, world_words=world_words,
         pair_counts=[len(t) for t in typed], static_pair_count=len(static_pairs),
         shape_names=[s[1] for s in shapes], pairs=all_pairs, tol=tol, unreachable_pairs=unreachable)
