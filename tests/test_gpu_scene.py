@@ -164,6 +164,18 @@ def test_held_object_modes(cuda_lib, name, parent, child):
     assert np.max(np.abs(pen.cpu().numpy() - open_)) < 2e-5
     base_free = model.check_configs(base_slot, torch.from_numpy(q).cuda()).cpu().numpy()
     assert (free.cpu().numpy() != base_free).any()  # the mode really changes the answer
+    # two-phase tiles in this mode: the held box is a moving box against the table (box-box records in phase A, their
+    # radii read through the pair ids); same flags as the single-pass kernel and as the full evaluation
+    be = model.device.be
+    qd = torch.from_numpy(q).cuda()
+    try:
+        be.set_two_phase(slot, "never")
+        single = be.check_configs(slot, qd).cpu().numpy()
+        be.set_two_phase(slot, "always")
+        two = be.check_configs(slot, qd).cpu().numpy()
+    finally:
+        be.set_two_phase(slot, "auto")
+    assert np.array_equal(single, two) and np.array_equal(two, free.cpu().numpy())
 
 
 def test_host_buffer_queries_equal_device_buffer_calls(be):
