@@ -632,20 +632,37 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
             k = par
         reach.append((c, r + bound_rs[i]))
 
+    any_bounded = any(math.isfinite(r) for _, r in reach)   # scenes of mobile bases: nothing to prune, skip the tests
+    reach_c = [tuple(float(v) for v in c) for c, _ in reach]  # plain floats: this runs once per pair and per mode
+    static_box = {}                                           # static index -> (centre, rows of R^T, half extents)
+    static_ctr = {}
+
     def never_meets(x: int, y: int, kind: int) -> bool:
-        cx, rx_ = reach[x]
+        if not any_bounded:
+            return False
+        rx_ = reach[x][1]
         if not math.isfinite(rx_):
             return False
+        cx = reach_c[x]
         if y < n_mov:
-            cy, ry_ = reach[y]
-            return math.isfinite(ry_) and float(np.linalg.norm(cx - cy)) > rx_ + ry_ + 2 * CULL_SLACK
+            ry_ = reach[y][1]
+            return math.isfinite(ry_) and math.dist(cx, reach_c[y]) > rx_ + ry_ + 2 * CULL_SLACK
         core, _, _, rad_y, data, _ = shape_rows[y]
         if core == CORE_BOX:  # distance from the reach centre to the static box itself (large tables)
-            ctr, R, half = np.array(data[:3]), np.array(data[3:12]).reshape(3, 3), np.array(data[12:15])
-            e = np.maximum(np.abs(R.T @ (cx - ctr)) - half, 0.0)
-            return float(np.linalg.norm(e)) > rx_ + rad_y + 2 * CULL_SLACK
-        ctr = 0.5 * (np.array(data[:3]) + np.array(data[3:6])) if core == CORE_SEG else np.array(data[:3])
-        return float(np.linalg.norm(cx - ctr)) > rx_ + bound_rs[y] + 2 * CULL_SLACK
+            if y not in static_box:
+                R = data[3:12]
+                static_box[y] = (data[:3], [(R[0 + k], R[3 + k], R[6 + k]) for k in range(3)], data[12:15])
+            ctr, cols, half = static_box[y]
+            d = (cx[0] - ctr[0], cx[1] - ctr[1], cx[2] - ctr[2])
+            e2 = 0.0
+            for k in range(3):
+                e = abs(cols[k][0] * d[0] + cols[k][1] * d[1] + cols[k][2] * d[2]) - half[k]
+                if e > 0.0:
+                    e2 += e * e
+            return math.sqrt(e2) > rx_ + rad_y + 2 * CULL_SLACK
+        if y not in static_ctr:
+            static_ctr[y] = tuple(0.5 * (data[k] + data[3 + k]) for k in range(3)) if core == CORE_SEG else tuple(data[:3])
+        return math.dist(cx, static_ctr[y]) > rx_ + bound_rs[y] + 2 * CULL_SLACK
 
     bp: List[List[List[Tuple[int, float, int]]]] = [[[] for _ in range(BP_SUBLISTS)] for _ in range(NUM_PAIR_TYPES)]
     unreachable: List[Tuple[str, str]] = []
