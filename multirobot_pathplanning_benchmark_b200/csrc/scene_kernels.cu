@@ -153,16 +153,18 @@ __device__ __forceinline__ void fk_phase(const uint32_t* bi, const float* q, flo
                 for (int k = 0; k < 3; k++) t[k] = nt[k];
             }
             const int code = bi[row + 1], qi = bi[row + 2];
-            float s, co;
+            float s = 0.f, co = 1.f;
+            // one copy of sincosf for the four rotating joint types (each inlined copy carries its own large-argument
+            // slow path: three copies less of it in the instruction stream)
+            if (code <= MRB_J_TRANS_XY_PHI) sincosf(q[code == MRB_J_TRANS_XY_PHI ? qi + 2 : qi], &s, &co);
             switch (code) {  // warp-uniform
-                case MRB_J_HINGE_X: sincosf(q[qi], &s, &co); rot_cols(R, 1, 2, co, s); break;
-                case MRB_J_HINGE_Y: sincosf(q[qi], &s, &co); rot_cols(R, 2, 0, co, s); break;
-                case MRB_J_HINGE_Z: sincosf(q[qi], &s, &co); rot_cols(R, 0, 1, co, s); break;
+                case MRB_J_HINGE_X: rot_cols(R, 1, 2, co, s); break;
+                case MRB_J_HINGE_Y: rot_cols(R, 2, 0, co, s); break;
+                case MRB_J_HINGE_Z: rot_cols(R, 0, 1, co, s); break;
                 case MRB_J_TRANS_XY_PHI: {
                     float x = q[qi], y = q[qi + 1];
 #pragma unroll
                     for (int r = 0; r < 3; r++) t[r] = fmaf(R[r * 3], x, fmaf(R[r * 3 + 1], y, t[r]));
-                    sincosf(q[qi + 2], &s, &co);
                     rot_cols(R, 0, 1, co, s);
                 } break;
                 // (constant column per case: a run-time column index would push R into local memory)
