@@ -409,6 +409,7 @@ SHAPE_WORDS = 20
 LARGE_BOX_BOUND = 0.3  # boxes with a bounding radius above this use the face-normal broadphase bound
 NUM_PAIR_TYPES = 8   # (point,point) (point,seg) (seg,seg) (point,box) (seg,box) (box,box) (cylz,cylz) (box,cylz)
 PAIR_TYPE = {(0, 0): 0, (0, 1): 1, (1, 1): 2, (0, 2): 3, (1, 2): 4, (2, 2): 5, (3, 3): 6, (2, 3): 7}
+DIRECT_TYPES = (6, 7)   # planar types the kernels evaluate straight from their pair lists (no broadphase records)
 PAIR_TYPE_NAMES = ["point-point", "point-seg", "seg-seg", "point-box", "seg-box", "box-box", "cylz-cylz", "box-cylz"]
 WORLD_WORDS = {CORE_POINT: 3, CORE_SEG: 6, CORE_BOX: 12, CORE_CYLZ: 3}
 # header word indices
@@ -666,7 +667,7 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
 
     bp: List[List[List[Tuple[int, float, int]]]] = [[[] for _ in range(BP_SUBLISTS)] for _ in range(NUM_PAIR_TYPES)]
     unreachable: List[Tuple[str, str]] = []
-    for t in range(NUM_PAIR_TYPES):
+    for t in range(NUM_PAIR_TYPES):   # (the planar direct types get records too; the kernels do not read them yet)
         for (ia, ib, kind) in typed[t]:
             x, y = (ia, ib) if ia < n_mov else (ib, ia)   # X is always a moving shape
             if t <= 5 and never_meets(x, y, kind):
@@ -690,7 +691,6 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
     # lists of the queued types (the kernels work from the records; the oracle and the host read these), static-static
     # pairs, per-shape robot ids, and the records' packed pair ids (one read per narrowphase item).
     n_shapes = len(shapes)
-    DIRECT_TYPES = (6, 7)
     off = HDR_WORDS
     off_frames = off
     off += FRAME_WORDS * len(frame_rows)
