@@ -280,7 +280,8 @@ def check_configs_host(be: SceneBackend, slot: int, q_host: torch.Tensor, out_ho
                        chunk: int = 1 << 19, state: Optional[dict] = None) -> None:
     """Host-buffer entry point (what a CPU-side caller of the reference API uses): q_host
     [B, D] float32 and out_host [B] uint8, both pinned.  Copies, kernels and read-backs of
-    consecutive chunks overlap on two streams; returns after everything has landed."""
+    consecutive chunks overlap on the side streams; returns after everything has landed in out_host (host-side
+    synchronisation of the side streams -- a CPU caller may read out_host right away)."""
     if q_host.is_cuda or out_host.is_cuda:
         raise ValueError("host tensors expected")
     B, D = q_host.shape
@@ -304,6 +305,7 @@ def check_configs_host(be: SceneBackend, slot: int, q_host: torch.Tensor, out_ho
             out_host[start:start + n].copy_(st["o"][k][:n], non_blocking=True)
     for s in st["streams"]:
         cur.wait_stream(s)
+        s.synchronize()
 
 
 def fp32_fma_peak_tflops(device=None, iters: int = 1 << 15, reps: int = 5) -> float:

@@ -46,9 +46,15 @@ struct ModeSlot {
 
 }  // namespace
 
+// The edge scheduler claims edges from a device counter.  Calls on one handle may come from several streams / host
+// threads, so every call takes its own counter from a ring (a counter is reused only after EDGE_COUNTERS further
+// calls on the handle; each use is reset on the caller's stream right before the launch).
+constexpr int EDGE_COUNTERS = 1024;
+
 struct mrb200_scene {
     std::vector<ModeSlot> slots;
-    int* counter = nullptr;  // device scratch for the edge scheduler
+    int* counter = nullptr;  // device scratch for the edge scheduler: ring of EDGE_COUNTERS ints
+    std::atomic<unsigned> counter_next{0};
     int* stats_dev = nullptr;   // [2 * slots] (configurations seen, decided in phase A) per mode slot
     int* stats_pin = nullptr;   // pinned copy, refreshed behind two-phase launches while a slot is still measuring
     // staging of the host-buffer query entry points (mrb200_query_*_host): one device and one pinned host
@@ -62,7 +68,8 @@ struct mrb200_scene {
 
 struct mrb200_abstract {
     mrb::AbstractSceneData data;
-    int* counter = nullptr;
+    int* counter = nullptr;   // ring of EDGE_COUNTERS ints, one per call (see mrb200_scene)
+    std::atomic<unsigned> counter_next{0};
     // mapped pinned staging of the host-buffer queries (mrb200_abstract_query_*_host), guarded by `mu`
     std::mutex mu;
     unsigned char* stage_pin = nullptr;
@@ -109,7 +116,7 @@ int mrb200_abstract_create(int n_agents, int dim, const double* radii, int n_sph
             env->data.rect_min[o][k] = rects[o * 2 * dim + k];
             env->data.rect_max[o][k] = rects[o * 2 * dim + dim + k];
         }
-    cudaError_t e = cudaMalloc(&env->counter, sizeof(int));
+    cudaError_t e = cudaMalloc(&env->counter, sizeof(int) * EDGE_COUNTERS);
     if (e != cudaSuccess) {
         delete env;
         return cuda_fail(e, "abstract_create");
@@ -136,14 +143,16 @@ int mrb200_abstract_check_configs(const mrb200_abstract_t* env, const double* q,
     return MRB200_OK;
 }
 
-int mrb200_abstract_check_edges(const mrb200_abstract_t* env, const double* q1, const double* q2, int64_t E,
+int mrb200_abstract_check_edges(const mrb200_abstract_t* env_c, const double* q1, const double* q2, int64_t E,
                                 double resolution, const int32_t* N_dev, int32_t n_start, int32_t n_max,
                                 int include_endpoints, uint8_t* free_dev, int32_t* first_pos_dev, mrb200_stream_t stream) {
+    mrb200_abstract_t* env = const_cast<mrb200_abstract_t*>(env_c);   // (only the counter ring index is touched)
     if (!env || E < 0 || (E && (!q1 || !q2 || !free_dev)) || n_start < 0 || (!N_dev && !(resolution > 0)))
         return fail(MRB200_ERR_ARG, "abstract_check_edges: bad argument");
     if (E == 0) return MRB200_OK;
+    int* counter = env->counter + env->counter_next.fetch_add(1, std::memory_order_relaxed) % EDGE_COUNTERS;
     cudaError_t e = mrb::launch_abstract_edges(env->data, q1, q2, E, resolution, N_dev, n_start, n_max, include_endpoints,
-                                               free_dev, first_pos_dev, env->counter, (cudaStream_t)stream);
+                                               free_dev, first_pos_dev, counter, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "abstract_check_edges");
     g_launches++;
     return MRB200_OK;
@@ -220,7 +229,7 @@ int mrb200_scene_create(int max_modes, mrb200_scene_t** out) {
                                                 cudaGetErrorString(e));
     auto* sc = new mrb200_scene();
     sc->slots.resize(max_modes);
-    e = cudaMalloc(&sc->counter, sizeof(int));
+    e = cudaMalloc(&sc->counter, sizeof(int) * EDGE_COUNTERS);
     if (e == cudaSuccess) e = cudaMalloc(&sc->stats_dev, 2 * sizeof(int) * max_modes);
     if (e == cudaSuccess) e = cudaMemset(sc->stats_dev, 0, 2 * sizeof(int) * max_modes);
     if (e == cudaSuccess) e = cudaHostAlloc(&sc->stats_pin, 2 * sizeof(int) * max_modes, cudaHostAllocDefault);
@@ -258,23 +267,44 @@ int mrb200_scene_set_mode(mrb200_scene_t* sc, int slot, const void* blob_host, s
         return fail(MRB200_ERR_BLOB, "scene_set_mode: inconsistent staged / tail split in the blob header");
     const int n_shapes = (int)(h[MRB_H_NMOV] + h[MRB_H_NSTA]);
     if (n_shapes > 256) return fail(MRB200_ERR_ARG, "scene_set_mode: more than 256 collision shapes");
+    // everything that can reject the blob is checked BEFORE the slot is touched
+    const int dof = (int)h[MRB_H_DOF];
+    if (dof < 1 || dof > 64) return fail(MRB200_ERR_ARG, "scene_set_mode: %d degrees of freedom (supported: 1..64)", dof);
+    if (mrb::scene_smem_bytes((int)h[MRB_H_STAGED_WORDS], dof, (int)h[MRB_H_WORLD_WORDS], n_shapes, 1) > 227 * 1024 ||
+        mrb::scene_smem_bytes((int)h[MRB_H_STAGED_WORDS], dof, (int)h[MRB_H_WORLD_WORDS], n_shapes, 2) > 227 * 1024)
+        return fail(MRB200_ERR_ARG, "scene_set_mode: scene needs more than 227 KB of shared memory per CTA");
     ModeSlot& s = sc->slots[slot];
     cudaStream_t st = (cudaStream_t)stream;
-    if (s.words != (int)h[MRB_H_TOTAL_WORDS]) {
-        cudaError_t e = cudaStreamSynchronize(st);
+    // Replacing a live slot: kernels launched earlier on OTHER streams (check_configs_host's side streams, other host
+    // threads) may still read the old blob, so wait for the whole device, not only for `stream`.
+    if (s.blob) {
+        cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode");
+    }
+    if (s.words != (int)h[MRB_H_TOTAL_WORDS]) {
         cudaFree(s.blob);
         s.blob = nullptr;
-        e = cudaMalloc(&s.blob, nbytes);
-        if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: cudaMalloc");
+        s.words = 0;          // the slot is empty until the new blob is fully in place
+        cudaError_t e = cudaMalloc(&s.blob, nbytes);
+        if (e != cudaSuccess) {
+            s.blob = nullptr;
+            return cuda_fail(e, "scene_set_mode: cudaMalloc");
+        }
     }
+    auto reset_slot = [&]() {
+        cudaFree(s.blob);
+        s.blob = nullptr;
+        s.words = 0;
+    };
     cudaError_t e = cudaMemcpyAsync(s.blob, blob_host, nbytes, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: copy");
-    e = cudaStreamSynchronize(st);  // blob_host may be pageable and freed by the caller
-    if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: sync");
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // blob_host may be pageable and freed by the caller
+    if (e != cudaSuccess) {
+        reset_slot();
+        return cuda_fail(e, "scene_set_mode: copy");
+    }
     s.words = (int)h[MRB_H_TOTAL_WORDS];
     s.staged = (int)h[MRB_H_STAGED_WORDS];
-    s.D = (int)h[MRB_H_DOF];
+    s.D = dof;
     s.world_words = (int)h[MRB_H_WORLD_WORDS];
     s.n_shapes = n_shapes;
     s.n_pairs = 0;
@@ -285,12 +315,11 @@ int mrb200_scene_set_mode(mrb200_scene_t* sc, int slot, const void* blob_host, s
     s.two_phase_forced = false;
     sc->stats_pin[2 * slot] = sc->stats_pin[2 * slot + 1] = 0;
     e = cudaMemsetAsync(sc->stats_dev + 2 * slot, 0, 2 * sizeof(int), st);
-    if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: counters");
-    if (mrb::scene_smem_bytes(s.staged, s.D, s.world_words, s.n_shapes, 1) > 227 * 1024 ||
-        mrb::scene_smem_bytes(s.staged, s.D, s.world_words, s.n_shapes, 2) > 227 * 1024)
-        return fail(MRB200_ERR_ARG, "scene_set_mode: scene needs more than 227 KB of shared memory per CTA");
-    e = mrb::launch_static_penetration(s.blob, st);
-    if (e != cudaSuccess) return cuda_fail(e, "scene_set_mode: static pairs");
+    if (e == cudaSuccess) e = mrb::launch_static_penetration(s.blob, st);
+    if (e != cudaSuccess) {
+        reset_slot();
+        return cuda_fail(e, "scene_set_mode: static pairs");
+    }
     g_launches++;
     return MRB200_OK;
 }
@@ -434,7 +463,7 @@ int mrb200_check_edges(const mrb200_scene_t* sc, int slot, const float* q1, cons
     p.tol = tol;
     p.flags = free_dev;
     p.first_pos = first_pos_dev;
-    p.counter = sc->counter;
+    p.counter = sc->counter + const_cast<mrb200_scene_t*>(sc)->counter_next.fetch_add(1, std::memory_order_relaxed) % EDGE_COUNTERS;
     cudaError_t e = mrb::launch_check_edges(p, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "check_edges");
     g_launches++;

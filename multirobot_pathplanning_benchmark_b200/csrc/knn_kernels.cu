@@ -306,6 +306,10 @@ static cudaError_t radius_t(const double* queries, const double* corpus, int64_t
     const size_t smem = (size_t)2 * TN * D * 8 + 16;
     const int64_t split_len = ((N + splits - 1) / splits + TN - 1) / TN * TN;
     dim3 grid((unsigned)((Q + KT - 1) / KT), (unsigned)splits);
+    if (smem > 48 * 1024) {   // D >= 48: above the default dynamic shared-memory limit
+        cudaError_t e = cudaFuncSetAttribute(radius_kernel<DMAX, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     radius_kernel<DMAX, FILL><<<grid, KT, smem, st>>>(queries, corpus, Q, N, D, sl, metric, radii, radius, inclusive, split_len, counts,
                                                       offsets, out_idx, out_dist, bulk_ok);
     return cudaGetLastError();

@@ -21,7 +21,11 @@ import numpy as np
 from .scene import CompiledScene, Scene, compile_blob
 from .scenes import SCENES
 
-try:  # the reference package (optional at import time)
+from .refimport import ensure_reference
+
+try:  # the reference package (optional at import time: baseline/_ref, /root/reference/src or a user's install)
+    if not ensure_reference():
+        raise ImportError("reference package not found")
     from multi_robot_multi_goal_planning.problems.planning_env import (  # type: ignore
         BaseModeLogic, BaseProblem, DependencyGraphMixin, Mode, SequenceMixin, State, Task, ProblemSpec, AgentType, ConstraintType,
         ManipulationType, DependencyType, DynamicsType, GoalType, SafePoseType, generate_binary_search_indices)
@@ -512,15 +516,24 @@ if HAVE_REFERENCE:
             by_mode: Dict[int, list] = {}
             for i, st in enumerate(path):
                 by_mode.setdefault(id(st.mode), [st.mode, [], []])
-                if check_start_and_end or 0 < i < L - 1 or (i == L - 1 and not check_edges_in_order and False):
+                # vertices the reference visits (planning_env.py:1791-1824 in-order: every vertex but the first when
+                # check_start_and_end is off, the last one always; :1827-1878 interleaved: the last one only with
+                # check_start_and_end)
+                if i == 0:
+                    vertex = check_start_and_end
+                elif i == L - 1:
+                    vertex = check_edges_in_order or check_start_and_end
+                else:
+                    vertex = True
+                if vertex:
                     by_mode[id(st.mode)][1].append(i)
                 if i + 1 < L:
                     by_mode[id(st.mode)][2].append(i)
             for mode, verts, edges in by_mode.values():
                 self.set_to_mode(mode)
-                if verts:
+                if verts:   # vertices are checked at the environment's own tolerance (is_collision_free(q, mode))
                     q = np.stack([np.asarray(path[i].q.state(), np.float32) for i in verts])
-                    if not bool(CudaDevice.to_numpy(self.model.device.check_configs(self._slot, q, tolerance)).all()):
+                    if not bool(CudaDevice.to_numpy(self.model.device.check_configs(self._slot, q, None)).all()):
                         return False
                 if edges:
                     q1 = np.stack([np.asarray(path[i].q.state(), np.float32) for i in edges])

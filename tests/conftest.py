@@ -26,21 +26,13 @@ def cuda_lib():
     return _lib.load()
 
 
-REFERENCE_SRC = "/root/reference/src"
-
-
 @pytest.fixture(scope="session")
 def reference():
-    """Makes the (read-only) reference importable, with MagicMock stubs for its GUI / rai
-    dependencies (recipe: SURVEY.md 8c).  Only exists in the build container; tests that need it
-    are skipped elsewhere (nothing under -m gpu depends on it)."""
-    if not os.path.isdir(REFERENCE_SRC):
-        pytest.skip("reference checkout not available")
-    from unittest.mock import MagicMock
-    for n in ("matplotlib", "matplotlib.pyplot", "matplotlib.animation", "matplotlib.patches", "matplotlib.collections",
-              "mpl_toolkits", "mpl_toolkits.mplot3d", "robotic", "simple_parsing"):
-        sys.modules.setdefault(n, MagicMock())
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    """Makes the reference importable (offline install under baseline/_ref, else the build container's read-only
+    checkout), with inert stand-ins for its GUI / rai dependencies (recipe: SURVEY.md 8c).  Tests that need it are
+    skipped where neither exists."""
+    from multirobot_pathplanning_benchmark_b200 import refimport
+    if not refimport.ensure_reference():
+        pytest.skip("reference package not available")
     import multi_robot_multi_goal_planning.problems as problems
     return problems

@@ -138,3 +138,89 @@ def test_batch_cost_matches_reference_golden(knn, golden, name):
     a = pts[::-1].copy()
     got = knn.batch_config_cost(torch.from_numpy(a).cuda(), torch.from_numpy(pts).cuda(), sl).cpu().numpy()
     assert np.array_equal(got, OA.batch_config_cost(a - pts, sl, "euclidean", "max"))
+
+
+# ---- BASELINE config 4 at its full size: 100k samples of one four-arm mode, D = 24 ----
+
+def _c4_corpus():
+    from multirobot_pathplanning_benchmark_b200.scenes import SCENES
+    lim = SCENES["box_stacking"][0]().limits()
+    return np.random.RandomState(5).uniform(lim[0], lim[1], (100_000, 24)), lim
+
+
+C4_SLICES = [[6 * r, 6 * r + 6] for r in range(4)]
+
+
+@pytest.mark.parametrize("metric", ["max_euclidean", "euclidean"])
+def test_knn_at_baseline_size_tensor_equals_exact_equals_oracle(knn, metric):
+    """north_star: "neighbour indices are bit-exact after re-rank" -- at N = Q = 100 000, D = 24, k* = 33
+    (prm_graph.py:440-445): the tcgen05 path and the fp64 CUDA-core path return identical indices and distances, and
+    200 sampled rows equal the reference's argpartition + argsort selection on the numba-order fp64 distances."""
+    corpus, _ = _c4_corpus()
+    k = knn.prm_k_star(len(corpus), 24)
+    assert k == 33
+    c = torch.from_numpy(corpus).cuda()
+    i_t, d_t = knn.batch_knn(c, c, C4_SLICES, metric, k, mode="tensor")
+    i_e, d_e = knn.batch_knn(c, c, C4_SLICES, metric, k, mode="exact")
+    assert torch.equal(i_t, i_e)
+    assert torch.equal(d_t, d_e)
+    assert torch.equal(i_t[:, 0].long(), torch.arange(len(corpus), device="cuda"))  # every sample is its own nearest neighbour
+    rows = np.random.default_rng(1).choice(len(corpus), 200, replace=False)
+    it, dt = i_t[torch.from_numpy(rows).cuda()].cpu().numpy(), d_t[torch.from_numpy(rows).cuda()].cpu().numpy()
+    sl = np.array(C4_SLICES)
+    for j, r in enumerate(rows):
+        d = OA.batch_config_dist(corpus[r], corpus, sl, metric)
+        want = OA.knn_indices(d, k)
+        assert np.array_equal(it[j], want)
+        assert np.array_equal(dt[j], d[want])
+
+
+def test_radius_at_baseline_size(knn):
+    """r-disc, the planners' default rule (composite_prm_planner.py:42): (i) the PRM* radius r* of prm_graph.py:479-500 at
+    N = 100 000, D = 24 -- in 24 dimensions it spans most of the space, so the answer is nearly the whole corpus per
+    query: bounded to 192 queries; (ii) a selective radius (the typical distance of the 33rd neighbour) for all 100 000
+    queries.  Rows against the reference's np.where selection, ascending index order."""
+    corpus, lim = _c4_corpus()
+    N, D = corpus.shape
+    c = torch.from_numpy(corpus).cuda()
+    sl = np.array(C4_SLICES)
+    r_star = knn.prm_r_star(N, D, float(np.prod(lim[1] - lim[0])))
+    q = c[:192].contiguous()
+    off, idx = knn.batch_radius(q, c, r_star, C4_SLICES, "max_euclidean")
+    off, idx = off.cpu().numpy(), idx.cpu().numpy()
+    for j in range(0, 192, 8):
+        d = OA.batch_config_dist(corpus[j], corpus, sl, "max_euclidean")
+        assert np.array_equal(idx[off[j]:off[j + 1]], OA.radius_indices(d, r_star))
+    assert off[-1] > 0.5 * 192 * N   # the PRM* radius really is that large here
+    # (ii) selective radius, every query
+    _, d33 = knn.batch_knn(c[:2048].contiguous(), c, C4_SLICES, "max_euclidean", 33)
+    r_sel = float(d33[:, -1].median().item())
+    off, idx, dist = knn.batch_radius(c, c, r_sel, C4_SLICES, "max_euclidean", return_dist=True)
+    off, idx, dist = off.cpu().numpy(), idx.cpu().numpy(), dist.cpu().numpy()
+    assert off.shape == (N + 1,) and (np.diff(off) >= 1).all()          # at least itself
+    assert 10 * N < off[-1] < 200 * N
+    assert (dist < r_sel).all()
+    for j in np.random.default_rng(2).choice(N, 200, replace=False):
+        d = OA.batch_config_dist(corpus[j], corpus, sl, "max_euclidean")
+        want = OA.radius_indices(d, r_sel)
+        assert np.array_equal(idx[off[j]:off[j + 1]], want)
+        assert np.array_equal(dist[off[j]:off[j + 1]], d[want])
+
+
+def test_radius_and_knn_at_the_largest_dimension(knn):
+    """D = 64 (KNN_MAX_D): the radius kernels' corpus tiles need more than the default 48 KB of dynamic shared memory"""
+    rng = np.random.default_rng(9)
+    D = 64
+    corpus, queries = rng.uniform(-1, 1, (3000, D)), rng.uniform(-1, 1, (50, D))
+    sl = [[16 * r, 16 * r + 16] for r in range(4)]
+    for metric in ("max_euclidean", "euclidean", "max"):
+        d0 = OA.batch_config_dist(queries[0], corpus, np.array(sl), metric)
+        r = float(np.sort(d0)[40])
+        off, idx = knn.batch_radius(torch.from_numpy(queries).cuda(), torch.from_numpy(corpus).cuda(), r, sl, metric)
+        off, idx = off.cpu().numpy(), idx.cpu().numpy()
+        for j in range(len(queries)):
+            d = OA.batch_config_dist(queries[j], corpus, np.array(sl), metric)
+            assert np.array_equal(idx[off[j]:off[j + 1]], OA.radius_indices(d, r))
+        i_k, _ = knn.batch_knn(torch.from_numpy(queries).cuda(), torch.from_numpy(corpus).cuda(), sl, metric, 9)
+        for j in range(0, len(queries), 7):
+            assert np.array_equal(i_k.cpu().numpy()[j], OA.knn_indices(OA.batch_config_dist(queries[j], corpus, np.array(sl), metric), 9))

@@ -10,9 +10,9 @@ import torch
 from multirobot_pathplanning_benchmark_b200 import scene as S
 from multirobot_pathplanning_benchmark_b200.scenes import SCENES
 from oracle import oracle_scene as O
+from tests.parity import MARGIN, edge_disagreements_are_inside_margin
 
 pytestmark = pytest.mark.gpu
-MARGIN = 1e-5
 
 
 @pytest.fixture(scope="module")
@@ -80,29 +80,63 @@ def test_unaligned_and_tiny_batches(be):
         assert f.shape == (B,) and np.array_equal(f.cpu().numpy(), want[:B])
 
 
-@pytest.mark.parametrize("name", ["2d_handover", "box_rearrangement", "mobile_wall_four", "abstract_like"])
+@pytest.mark.parametrize("name", ["2d_handover", "box_rearrangement", "box_stacking", "mobile_wall_four", "abstract_like"])
 def test_edges(be, name):
     slot, sc, cs, kw = be.scenes[name]
-    E = 1500 if name != "box_rearrangement" else 600
+    E = {"box_rearrangement": 600, "box_stacking": 400}.get(name, 1500)
     q1 = uniform_configs(sc, E, 10)
     q2 = uniform_configs(sc, E, 11)
     q2[::2] = q1[::2] + np.random.default_rng(1).uniform(-0.15, 0.15, q1[::2].shape).astype(np.float32)
+    if name == "box_stacking":   # uniform four-arm samples nearly always collide: start the local half from free samples
+        pool = uniform_configs(sc, 60_000, 12)
+        pool = pool[be.check_configs(slot, torch.from_numpy(pool).cuda()).cpu().numpy().astype(bool)]
+        n = min(len(pool), len(q1[::2]))
+        q1[:2 * n:2] = pool[:n]
+        q2[:2 * n:2] = pool[:n] + np.random.default_rng(2).uniform(-0.1, 0.1, pool[:n].shape).astype(np.float32)
     res = kw["resolution"]
     free, first = be.check_edges(slot, torch.from_numpy(q1).cuda(), torch.from_numpy(q2).cuda(), res)
     free, first = free.cpu().numpy(), first.cpu().numpy()
     ofree, ofirst, _ = O.check_edges(cs.blob64, q1.astype(np.float64), q2.astype(np.float64), res, nthreads=O.max_threads())
-    agree = free == ofree
     # an edge may only disagree if one of its interpolated configurations is inside the margin
-    for e in np.nonzero(~agree | (first != ofirst))[0]:
-        N = max(2, int(np.max(np.abs(q1[e].astype(np.float64) - q2[e].astype(np.float64))) / res) + 1)
-        idx = O.binary_indices(N)
-        d = (q2[e].astype(np.float64) - q1[e].astype(np.float64)) / (N - 1)
-        ii = idx[(idx != 0) & (idx != N - 1)].astype(np.float64)
-        qs = q1[e].astype(np.float64)[None] + d[None] * ii[:, None]
-        _, p, md = O.check_configs(cs.blob64, qs)
-        assert np.min(np.abs(O.margin(p, md, cs.tol))) <= MARGIN, f"edge {e}: flags differ with all samples margin-clear"
-    assert agree.mean() > 0.995
+    n_diff = edge_disagreements_are_inside_margin(cs, q1, q2, res, free, first, ofree, ofirst)
+    assert n_diff <= 0.005 * E + 2
     assert 0.02 < free.mean() < 0.98
+
+
+@pytest.mark.parametrize("name,parent,child", [("box_rearrangement", "a1_ur_vacuum", "obj11"), ("2d_handover", "a1", "obj1"),
+                                               ("mobile_wall_four", "a0_gripper", "obj_00"), ("box_stacking", "a2_ur_gripper_center", "obj00")])
+def test_edges_in_held_object_modes(cuda_lib, name, parent, child):
+    """A8 in a mode whose kinematic tree carries an object on a robot link (A7): uniform edges and planner-like local
+    edges from free configurations, flags and first colliding positions against the oracle on the same compiled tree."""
+    from multirobot_pathplanning_benchmark_b200.env import SceneModel
+    mk, kw = SCENES[name]
+    sc = mk()
+    model = SceneModel(sc, kw["tol"], kw["resolution"])
+    rng = np.random.default_rng(8)
+    lim = sc.limits()
+    base_slot = model.slot_for(())
+    cand = rng.uniform(lim[0], lim[1], (8192, sc.dof)).astype(np.float32)
+    ok = model.check_configs(base_slot, cand).cpu().numpy()
+    slot = model.slot_for(("held",), [(parent, child, cand[np.argmax(ok)].astype(np.float64))])
+    cs = model.compiled(slot)
+    be = model.device.be
+    pool = uniform_configs(sc, 80_000, 13)
+    pool = pool[be.check_configs(slot, torch.from_numpy(pool).cuda()).cpu().numpy().astype(bool)]
+    assert len(pool) >= 50
+    n_loc = min(len(pool), 400)
+    E_uni = 200 if name in ("box_stacking", "box_rearrangement") else 600
+    q1 = np.vstack([pool[:n_loc], uniform_configs(sc, E_uni, 14)])
+    q2 = np.vstack([pool[:n_loc] + rng.uniform(-0.12, 0.12, (n_loc, sc.dof)).astype(np.float32), uniform_configs(sc, E_uni, 15)])
+    res = kw["resolution"]
+    free, first = be.check_edges(slot, torch.from_numpy(q1).cuda(), torch.from_numpy(q2).cuda(), res)
+    free, first = free.cpu().numpy(), first.cpu().numpy()
+    ofree, ofirst, _ = O.check_edges(cs.blob64, q1.astype(np.float64), q2.astype(np.float64), res, nthreads=O.max_threads())
+    n_diff = edge_disagreements_are_inside_margin(cs, q1, q2, res, free, first, ofree, ofirst)
+    assert n_diff <= 0.01 * len(q1) + 2
+    assert free[:n_loc].any() and not free.all()
+    # the same edges in the start mode give different answers somewhere: the held object matters
+    bfree, _ = be.check_edges(base_slot, torch.from_numpy(q1).cuda(), torch.from_numpy(q2).cuda(), res)
+    assert (bfree.cpu().numpy() != free).any()
 
 
 def test_edge_windows_and_explicit_N(be):
@@ -113,13 +147,15 @@ def test_edge_windows_and_explicit_N(be):
         f, p = be.check_edges(slot, t1, t2, 0.01, n_start=ns, n_max=nm, include_endpoints=inc)
         of, op, _ = O.check_edges(cs.blob64, q1.astype(np.float64), q2.astype(np.float64), 0.01, n_start=ns,
                                   n_max=-1 if nm is None else nm, include_endpoints=inc)
-        assert (f.cpu().numpy() == of).mean() > 0.99
-        same = f.cpu().numpy() == of
-        assert np.array_equal(p.cpu().numpy()[same & ~of], op[same & ~of]) or (p.cpu().numpy()[same] == op[same]).mean() > 0.99
-    N = torch.full((400,), 25, dtype=torch.int32, device="cuda")
-    f, _ = be.check_edges(slot, t1, t2, 0.01, N=N)
-    of, _, chk = O.check_edges(cs.blob64, q1.astype(np.float64), q2.astype(np.float64), 0.01, Ns=np.full(400, 25, np.int32))
-    assert (f.cpu().numpy() == of).mean() > 0.99 and chk.max() <= 23
+        n_diff = edge_disagreements_are_inside_margin(cs, q1, q2, 0.01, f.cpu().numpy(), p.cpu().numpy(), of, op, n_start=ns,
+                                                      n_max=nm, include_endpoints=inc)
+        assert n_diff <= 4
+    Nh = np.full(400, 25, np.int32)
+    N = torch.from_numpy(Nh).cuda()
+    f, p = be.check_edges(slot, t1, t2, 0.01, N=N)
+    of, op, chk = O.check_edges(cs.blob64, q1.astype(np.float64), q2.astype(np.float64), 0.01, Ns=Nh)
+    assert edge_disagreements_are_inside_margin(cs, q1, q2, 0.01, f.cpu().numpy(), p.cpu().numpy(), of, op, Ns=Nh) <= 4
+    assert chk.max() <= 23
 
 
 def test_for_robot_rule(be):
@@ -241,17 +277,17 @@ def test_edge_kernel_corner_cases(be):
         a = free_q[:n]
         b = free_q[1000:1000 + n]
         f, p, of, op = both(a, b)
-        assert (f == of).all() and np.array_equal(p[f == of], op[f == of])
+        edge_disagreements_are_inside_margin(cs, a, b, 0.01, f, p, of, op)
     # (3) explicit N of wildly different sizes in one batch, including the minimum
     n = 2000
     a, b = free_q[:n], free_q[2000:2000 + n]
     N = rng.choice([2, 3, 5, 31, 32, 33, 64, 700], n).astype(np.int32)
     f, p, of, op = both(a, b, N=N)
-    assert (f == of).mean() > 0.995 and np.array_equal(p[f == of], op[f == of])
+    assert edge_disagreements_are_inside_margin(cs, a, b, 0.01, f, p, of, op, Ns=N) <= 10
     # (4) windows: empty (n_start = n_max), beyond the end, and a late start
     for ns, nm in ((5, 5), (0, 100000), (40, None), (3, 4)):
         f, p, of, op = both(a, b, N=N, n_start=ns, n_max=nm)
-        assert (f == of).mean() > 0.995 and np.array_equal(p[f == of], op[f == of]), (ns, nm)
+        assert edge_disagreements_are_inside_margin(cs, a, b, 0.01, f, p, of, op, Ns=N, n_start=ns, n_max=nm) <= 10, (ns, nm)
         if ns == nm:
             assert f.all() and (p == -1).all()
     # (5) far more edges than resident CTAs x slots, all short: every edge gets exactly one answer
@@ -263,7 +299,7 @@ def test_edge_kernel_corner_cases(be):
     assert f.shape == (big,) and set(np.unique(f.cpu().numpy())) <= {0, 1}
     sub = rng.integers(0, big, 3000)
     of, op, _ = O.check_edges(cs.blob64, a[sub].astype(np.float64), b[sub].astype(np.float64), 0.01)
-    assert (f.cpu().numpy()[sub] == of).mean() > 0.995
+    assert edge_disagreements_are_inside_margin(cs, a[sub], b[sub], 0.01, f.cpu().numpy()[sub], p.cpu().numpy()[sub], of, op) <= 15
 
 
 def test_informed_batch_sampler_prunes_on_the_device(cuda_lib):

@@ -63,13 +63,19 @@ def test_full_batch_is_order_and_chunk_invariant_and_matches_oracle_sample(be, n
     assert np.max(np.abs(pen[idx].cpu().numpy() - open_)) < 2e-5
 
 
-@pytest.mark.parametrize("name,E", [("2d_handover", 100_000), ("box_rearrangement", 40_000), ("mobile_wall_four", 40_000)])
+@pytest.mark.parametrize("name,E", [("2d_handover", 100_000), ("box_rearrangement", 40_000), ("box_stacking", 20_000),
+                                    ("mobile_wall_four", 40_000)])
 def test_edges_equal_config_kernel_on_the_reference_interpolation_points(be, name, E):
     """edge free <=> every interior interpolation point free, first colliding position = first hit in the
     reference's binary order; both sides on the device, inputs bit-identical, so the agreement is exact."""
     slot, sc, cs, kw = be.scenes[name]
     res = kw["resolution"]
     q1 = uniform_device(sc, E, 5)
+    if name == "box_stacking":   # uniform four-arm samples nearly always collide: start half of the edges from free samples
+        pool = uniform_device(sc, 40 * E, 4)
+        pool = pool[be.check_configs(slot, pool).bool()]
+        n = min(pool.shape[0], E // 2)
+        q1[:n] = pool[:n]
     step = (torch.rand((E, sc.dof), device="cuda", generator=torch.Generator(device="cuda").manual_seed(6)) - 0.5)
     scale = torch.rand((E, 1), device="cuda", generator=torch.Generator(device="cuda").manual_seed(7)) * 1.2
     q2 = q1 + step * scale  # planner-like edges: 0 .. 0.6 rad per joint, N = 2 .. ~60 (120 on the 0.02 scene)
@@ -95,4 +101,4 @@ def test_edges_equal_config_kernel_on_the_reference_interpolation_points(be, nam
         order = O.binary_indices(int(N_h[e]))
         pos = next(p for p, idx in enumerate(order) if 0 < idx < N_h[e] - 1 and hit_h[e, idx])
         assert first_h[e] == pos, (e, first_h[e], pos)
-    assert 0.05 < free.float().mean().item() < 0.99
+    assert (0.02 if name == "box_stacking" else 0.05) < free.float().mean().item() < 0.99
