@@ -40,8 +40,8 @@ const char* mrb200_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t mrb200_launch_count(void);
 
-/* FP32 FMA roofline probe (measurement aid for bench.py): runs n_threads threads x iters x 8
- * dependent-chain FMAs; out_dev holds n_threads floats (pass NULL to only query n_threads). */
+/* FP32 FMA roofline probe (measurement aid for bench.py): runs n_threads threads x iters x 16
+ * FMAs (16 independent chains per thread, iters rounded up to a multiple of 16); out_dev holds n_threads floats (pass NULL to only query n_threads). */
 int mrb200_fp32_probe(int iters, float* out_dev, int32_t* n_threads, mrb200_stream_t stream);
 
 /* ---- sphere-agent environment: AbstractEnvironment, P/problems/abstract_env.py:112-354 ----
@@ -111,6 +111,16 @@ int mrb200_query_edges_host(mrb200_scene_t* scene, int slot, const float* q1_hos
                             double resolution, const int32_t* N_host, int32_t n_start, int32_t n_max,
                             int include_endpoints, float tol, uint8_t* free_host, int32_t* first_pos_host,
                             mrb200_stream_t stream);
+/* Asynchronous edge batches with HOST buffers -- the seam behind env.py's speculation of a PRM / EIT* node's candidate
+ * edges (P/planners/prm/prm_graph.py:675 checks them lazily, one call each, right after get_neighbors :389-549 has
+ * named them all).  submit: inputs are copied into a pinned buffer owned by the handle, H2D + kernel + D2H are queued on
+ * `stream`, an event is recorded and the call returns with a ticket.  q1_host holds q1_rows = 1 (one start for all edges)
+ * or E rows.  Whole edges only (no window).  collect: waits for the ticket's event, writes free_host[E] and
+ * first_pos_host[E] (nullable).  A ticket expires after 8 further submits on the handle. */
+int mrb200_submit_edges_host(mrb200_scene_t* scene, int slot, const float* q1_host, int q1_rows, const float* q2_host,
+                             int64_t E, double resolution, const int32_t* N_host, int include_endpoints, float tol,
+                             int64_t* ticket_out, mrb200_stream_t stream);
+int mrb200_collect_edges_host(mrb200_scene_t* scene, int64_t ticket, int64_t E, uint8_t* free_host, int32_t* first_pos_host);
 /* introspection of a slot: D, n_shapes, n_pairs (dynamic), shared memory bytes per CTA */
 int mrb200_scene_info(const mrb200_scene_t* scene, int slot, int32_t* out4);
 /* Large plain batches (mrb200_check_configs, B >= 4096, no penetration output) can run as two-phase tiles: a cheap

@@ -268,6 +268,32 @@ class SceneBackend:
             _lib.check(rc, "query_edges_host")
         return free, first
 
+    # ---- asynchronous host-buffer edge batches (candidate-edge speculation of env.py) ----
+    def submit_edges_host(self, slot: int, q1: np.ndarray, q2: np.ndarray, resolution: float, N: Optional[np.ndarray] = None,
+                          include_endpoints: bool = False, tol: Optional[float] = None) -> int:
+        """q1 [D] or [E, D], q2 [E, D] (numpy); queues copies + kernel on the current stream and returns a ticket"""
+        q2 = np.ascontiguousarray(q2, np.float32)
+        q1 = np.ascontiguousarray(q1, np.float32).reshape(-1, q2.shape[1])
+        if q2.ndim != 2 or q2.shape[1] != self.compiled[slot].dof or q1.shape[0] not in (1, q2.shape[0]):
+            raise ValueError("q1 must be [D] or [E, D] and q2 [E, D]")
+        Nh = None if N is None else np.ascontiguousarray(N, np.int32)
+        ticket = C.c_int64(-1)
+        with self._on_device():
+            rc = self.lib.mrb200_submit_edges_host(
+                self.handle, slot, q1.ctypes.data, q1.shape[0], q2.ctypes.data, q2.shape[0], float(resolution),
+                Nh.ctypes.data if Nh is not None else None, int(include_endpoints), -1.0 if tol is None else float(tol),
+                C.byref(ticket), _stream(self.device))
+        if rc:
+            _lib.check(rc, "submit_edges_host")
+        return int(ticket.value)
+
+    def collect_edges_host(self, ticket: int, E: int):
+        free, first = np.empty(E, np.uint8), np.empty(E, np.int32)
+        rc = self.lib.mrb200_collect_edges_host(self.handle, int(ticket), int(E), free.ctypes.data, first.ctypes.data)
+        if rc:
+            _lib.check(rc, "collect_edges_host")
+        return free, first
+
     def _on_device(self):
         """device guard that costs nothing when this backend's GPU already is the current one (the latency-critical
         single-query path)"""
@@ -309,7 +335,7 @@ def check_configs_host(be: SceneBackend, slot: int, q_host: torch.Tensor, out_ho
 
 
 def fp32_fma_peak_tflops(device=None, iters: int = 1 << 15, reps: int = 5) -> float:
-    """Measured FP32 FMA throughput of this GPU (8 independent chains per thread)."""
+    """Measured FP32 FMA throughput of this GPU (16 independent chains per thread, `iters` a multiple of 16)."""
     lib = _lib.load()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     n = C.c_int32()
@@ -323,7 +349,7 @@ def fp32_fma_peak_tflops(device=None, iters: int = 1 << 15, reps: int = 5) -> fl
             _lib.check(lib.mrb200_fp32_probe(iters, out.data_ptr(), C.byref(n), _stream(device)), "fp32_probe")
             e1.record()
             e1.synchronize()
-            best = max(best, n.value * iters * 16.0 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+            best = max(best, n.value * iters * 32.0 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
 
 

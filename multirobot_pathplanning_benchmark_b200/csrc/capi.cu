@@ -55,6 +55,19 @@ struct mrb200_scene {
     std::vector<ModeSlot> slots;
     int* counter = nullptr;  // device scratch for the edge scheduler: ring of EDGE_COUNTERS ints
     std::atomic<unsigned> counter_next{0};
+    // asynchronous host-buffer edge batches (mrb200_submit_edges_host / mrb200_collect_edges_host): a ring of tickets,
+    // each with its own pinned + device staging and an event; guarded by `mu`
+    struct EdgeTicket {
+        cudaEvent_t ev = nullptr;
+        unsigned char* dev = nullptr;
+        unsigned char* pin = nullptr;
+        size_t bytes = 0, out_off = 0, nb = 0;
+        int64_t E = 0, seq = -1;
+        bool pending = false;
+    };
+    static constexpr int N_TICKETS = 8;
+    EdgeTicket tickets[N_TICKETS];
+    int64_t ticket_seq = 0;
     int* stats_dev = nullptr;   // [2 * slots] (configurations seen, decided in phase A) per mode slot
     int* stats_pin = nullptr;   // pinned copy, refreshed behind two-phase launches while a slot is still measuring
     // staging of the host-buffer query entry points (mrb200_query_*_host): one device and one pinned host
@@ -252,6 +265,11 @@ int mrb200_scene_destroy(mrb200_scene_t* sc) {
     cudaFreeHost(sc->stats_pin);
     cudaFree(sc->stage_dev);
     cudaFreeHost(sc->stage_pin);
+    for (auto& t : sc->tickets) {
+        if (t.ev) cudaEventDestroy(t.ev);
+        cudaFree(t.dev);
+        cudaFreeHost(t.pin);
+    }
     delete sc;
     return MRB200_OK;
 }
@@ -563,6 +581,81 @@ int mrb200_query_edges_host(mrb200_scene_t* sc, int slot, const float* q1_host, 
     if (e != cudaSuccess) return cuda_fail(e, "query_edges_host: D2H");
     if (first_pos_host) memcpy(first_pos_host, sc->stage_pin + 2 * qb + nb, (size_t)E * 4);
     memcpy(free_host, sc->stage_pin + 2 * qb + 2 * nb, (size_t)E);
+    return MRB200_OK;
+}
+
+// Asynchronous edge batches with host buffers: submit copies the inputs into a library-owned pinned buffer, queues
+// H2D copy + kernel + D2H copy on `stream`, records an event and returns at once with a ticket; collect waits for the
+// event and hands the results out.  The caller (env.py's speculation of a PRM node's candidate edges) overlaps the
+// device work with the planner's own host work.  A ticket stays valid until N_TICKETS further submits on the handle.
+int mrb200_submit_edges_host(mrb200_scene_t* sc, int slot, const float* q1_host, int q1_rows, const float* q2_host, int64_t E,
+                             double resolution, const int32_t* N_host, int include_endpoints, float tol, int64_t* ticket_out,
+                             mrb200_stream_t stream) {
+    const ModeSlot* s = get_slot(sc, slot);
+    if (!s) return fail(MRB200_ERR_ARG, "submit_edges_host: empty mode slot %d", slot);
+    if (E < 1 || !q1_host || !q2_host || !ticket_out || (q1_rows != 1 && q1_rows != E))
+        return fail(MRB200_ERR_ARG, "submit_edges_host: bad argument (q1 is one row or one row per edge)");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lock(sc->mu);
+    const int64_t seq = sc->ticket_seq++;
+    auto& t = sc->tickets[seq % mrb200_scene::N_TICKETS];
+    cudaError_t e = cudaSuccess;
+    if (!t.ev) e = cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming);
+    if (e == cudaSuccess && t.pending) e = cudaEventSynchronize(t.ev);   // an uncollected older batch: its results are dropped
+    if (e != cudaSuccess) return cuda_fail(e, "submit_edges_host: event");
+    t.pending = false;
+    const size_t row = (size_t)s->D * 4;
+    const size_t qb = up16((size_t)E * row), nb = up16((size_t)E * 4), fb = up16((size_t)E);
+    const size_t need = 2 * qb + 2 * nb + fb;     // q1 | q2 | N | first | free
+    if (need > t.bytes) {
+        cudaFree(t.dev);
+        cudaFreeHost(t.pin);
+        t.dev = t.pin = nullptr;
+        t.bytes = 0;
+        size_t cap = 1 << 16;
+        while (cap < need) cap *= 2;
+        e = cudaMalloc(&t.dev, cap);
+        if (e == cudaSuccess) e = cudaHostAlloc(&t.pin, cap, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaFree(t.dev);
+            t.dev = nullptr;
+            return cuda_fail(e, "submit_edges_host: staging");
+        }
+        t.bytes = cap;
+    }
+    if (q1_rows == 1) for (int64_t i = 0; i < E; i++) memcpy(t.pin + (size_t)i * row, q1_host, row);
+    else memcpy(t.pin, q1_host, (size_t)E * row);
+    memcpy(t.pin + qb, q2_host, (size_t)E * row);
+    if (N_host) memcpy(t.pin + 2 * qb, N_host, (size_t)E * 4);
+    e = cudaMemcpyAsync(t.dev, t.pin, 2 * qb + (N_host ? nb : 0), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "submit_edges_host: H2D");
+    int rc = mrb200_check_edges(sc, slot, (const float*)t.dev, (const float*)(t.dev + qb), E, resolution,
+                                N_host ? (const int32_t*)(t.dev + 2 * qb) : nullptr, 0, -1, include_endpoints, tol,
+                                t.dev + 2 * qb + 2 * nb, (int32_t*)(t.dev + 2 * qb + nb), stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(t.pin + 2 * qb + nb, t.dev + 2 * qb + nb, nb + fb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(t.ev, st);
+    if (e != cudaSuccess) return cuda_fail(e, "submit_edges_host: D2H");
+    t.E = E;
+    t.seq = seq;
+    t.out_off = 2 * qb + nb;
+    t.nb = nb;
+    t.pending = true;
+    *ticket_out = seq;
+    return MRB200_OK;
+}
+
+int mrb200_collect_edges_host(mrb200_scene_t* sc, int64_t ticket, int64_t E, uint8_t* free_host, int32_t* first_pos_host) {
+    if (!sc || ticket < 0 || !free_host) return fail(MRB200_ERR_ARG, "collect_edges_host: bad argument");
+    std::lock_guard<std::mutex> lock(sc->mu);
+    auto& t = sc->tickets[ticket % mrb200_scene::N_TICKETS];
+    if (t.seq != ticket || !t.pending || t.E != E)
+        return fail(MRB200_ERR_ARG, "collect_edges_host: ticket %lld expired or already collected", (long long)ticket);
+    cudaError_t e = cudaEventSynchronize(t.ev);
+    if (e != cudaSuccess) return cuda_fail(e, "collect_edges_host");
+    if (first_pos_host) memcpy(first_pos_host, t.pin + t.out_off, (size_t)E * 4);
+    memcpy(free_host, t.pin + t.out_off + t.nb, (size_t)E);
+    t.pending = false;
     return MRB200_OK;
 }
 

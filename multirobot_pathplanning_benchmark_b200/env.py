@@ -87,6 +87,13 @@ class CudaDevice:
         return self.be.query_edges_host(slot, q1, q2, resolution, N=N, n_start=n_start, n_max=n_max,
                                         include_endpoints=include_endpoints, tol=tol)
 
+    # asynchronous whole-edge batches (candidate-edge speculation): -> ticket, later (free, first colliding position)
+    def prefetch_edges(self, slot, q1, q2, resolution, N=None, include_endpoints=False, tol=None):
+        return self.be.submit_edges_host(slot, q1, q2, resolution, N=N, include_endpoints=include_endpoints, tol=tol)
+
+    def collect_edges(self, ticket, E):
+        return self.be.collect_edges_host(ticket, E)
+
     @staticmethod
     def to_numpy(x):
         return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
@@ -112,27 +119,85 @@ class SpeculativeCache:
         colliding position p0; a window [a, b) is free iff p0 is none or p0 >= b, collides iff a <= p0 < b,
         and only a window that starts after a known collision goes back to the device.
 
+      * pinned samples: transition sampling overwrites some robots' coordinates of a block row with their goal values
+        before asking (`_apply_pinned`, P/planners/collision_free_sampler.py:99-110; composite_prm_planner.py:300-303),
+        so the exact-row lookup misses.  The sampler hands rows out in order, so the query is compared with the row
+        handed out last: if it differs only in a set of coordinates, the remaining rows of the block are validated with
+        the same coordinates overwritten, in one launch -- the following transition samples of that mode hit.
+      * candidate edges: the PRM search expands a node by asking for its neighbours and their edge costs
+        (`env.batch_config_cost(node.q, neighbour_array)`, P/planners/prm/prm_graph.py:706-712) and afterwards checks
+        the candidate edges lazily, one `is_edge_collision_free` call per queue pop (:666-677).  The cost call names
+        every candidate edge of the node, so all of them go to the device in ONE asynchronous launch
+        (mrb200_submit_edges_host) while the planner pushes them onto its queue; the later single queries are answered
+        from the batch's first colliding positions.  A batch issued for the wrong kinematic tree (the node was a
+        transition twin) is re-issued once for the right one.
+
     Keys are the exact fp64 bytes of the configurations, so a configuration that was edited after sampling
     (pinned robots) simply misses the cache and takes the normal path."""
 
-    def __init__(self, max_edges: int = 1 << 18):
+    class Candidates:
+        """one node's candidate edges: start q1, ends q2 [E, D], per-edge N, the launch parameters and (once collected)
+        the first colliding positions"""
+        __slots__ = ("slot", "q2", "N", "params", "ticket", "first", "index")
+
+        def __init__(self, slot, q2, N, params, ticket):
+            self.slot, self.q2, self.N, self.params, self.ticket = slot, q2, N, params, ticket
+            self.first = None
+            self.index = None
+
+        def row_of(self, q2_bytes: bytes) -> Optional[int]:
+            if self.index is None:   # built on the first lookup, one vectorised pass
+                rows = np.ascontiguousarray(self.q2).view(np.dtype((np.void, self.q2.shape[1] * 8))).ravel().tolist()
+                self.index = {}
+                for i, r in enumerate(rows):
+                    self.index.setdefault(r, i)
+            return self.index.get(q2_bytes)
+
+    def __init__(self, max_edges: int = 1 << 18, max_candidate_batches: int = 256):
         self.block: Optional[np.ndarray] = None
-        self.block_index: Dict[bytes, int] = {}
+        self.block_index: Optional[Dict[bytes, int]] = None
         self.block_flags: Dict[int, np.ndarray] = {}
         self.edges: Dict[tuple, int] = {}
         self.max_edges = max_edges
-        self.stats = {"config_launches": 0, "config_hits": 0, "edge_launches": 0, "edge_hits": 0}
+        # start configuration -> its latest batches (a transition configuration is expanded twice: as the node of the
+        # mode it ends and as its twin in the mode it starts, with different neighbour sets)
+        self.candidates: Dict[bytes, List["SpeculativeCache.Candidates"]] = {}
+        self.max_candidate_batches = max_candidate_batches
+        self.cursor = 0                       # index of the block row handed out last
+        self.pinned_flags: Dict[tuple, tuple] = {}   # (slot, changed coordinates, their values) -> (first row, flags)
+        self.stats = {"config_launches": 0, "config_hits": 0, "pinned_launches": 0, "pinned_hits": 0, "edge_launches": 0, "edge_hits": 0,
+                      "candidate_batches": 0, "candidate_edges": 0, "candidate_hits": 0, "candidate_reissues": 0}
 
     def new_block(self, batch: np.ndarray) -> None:
         self.block = batch
-        self.block_index = {batch[i].tobytes(): i for i in range(len(batch))}
+        self.block_index = None     # row lookup table, built on the first query of the block (one vectorised pass)
         self.block_flags = {}
+        self.pinned_flags = {}
+        self.cursor = 0
+
+    def _block_row(self, q_state: np.ndarray) -> Optional[int]:
+        if self.block is None:
+            return None
+        if self.block_index is None:
+            b = np.ascontiguousarray(self.block)
+            rows = b.view(np.dtype((np.void, b.shape[1] * 8))).ravel().tolist()
+            self.block_index = dict(zip(rows, range(len(rows))))
+        return self.block_index.get(np.ascontiguousarray(q_state, np.float64).tobytes())
+
+    def add_candidates(self, q1_bytes: bytes, cand: "SpeculativeCache.Candidates") -> None:
+        if len(self.candidates) >= self.max_candidate_batches:
+            for k in list(self.candidates)[: self.max_candidate_batches // 2]:   # oldest half (insertion order)
+                del self.candidates[k]
+        lst = self.candidates.pop(q1_bytes, [])
+        self.candidates[q1_bytes] = ([cand] + lst)[:4]
+        self.stats["candidate_batches"] += 1
+        self.stats["candidate_edges"] += len(cand.N)
 
     def config_flag(self, slot: int, q_state: np.ndarray, check_batch) -> Optional[bool]:
         """flag of a configuration of the current sample block in mode slot `slot`, or None if it is not one"""
-        i = self.block_index.get(np.ascontiguousarray(q_state, np.float64).tobytes())
+        i = self._block_row(q_state)
         if i is None:
-            return None
+            return self._pinned_flag(slot, q_state, check_batch)
         flags = self.block_flags.get(slot)
         if flags is None:
             flags = np.asarray(check_batch(self.block)).astype(bool)
@@ -142,15 +207,42 @@ class SpeculativeCache:
             self.stats["config_hits"] += 1
         return bool(flags[i])
 
+    def _pinned_flag(self, slot: int, q_state: np.ndarray, check_batch) -> Optional[bool]:
+        """the row handed out last with some coordinates overwritten (pinned robots)?  Then validate the rest of the block
+        with the same overwrite."""
+        if self.block is None or not (0 <= self.cursor < len(self.block)):
+            return None
+        q = np.asarray(q_state, np.float64)
+        row = self.block[self.cursor]
+        if q.shape != row.shape:
+            return None
+        diff = q != row
+        n = int(diff.sum())
+        if n == 0 or n == len(q):
+            return None
+        key = (slot, diff.tobytes(), q[diff].tobytes())
+        hit = self.pinned_flags.get(key)
+        if hit is None:
+            batch = self.block[self.cursor:].copy()
+            batch[:, diff] = q[diff]
+            hit = (self.cursor, np.asarray(check_batch(batch)).astype(bool))
+            if len(self.pinned_flags) >= 64:
+                self.pinned_flags.clear()
+            self.pinned_flags[key] = hit
+            self.stats["pinned_launches"] += 1
+        else:
+            self.stats["pinned_hits"] += 1
+        first, flags = hit
+        return bool(flags[self.cursor - first])
+
     def edge_window(self, key: tuple, n_start: int, n_max: Optional[int], N: int, full_scan) -> Optional[bool]:
         """answer for window [n_start, n_max) of the edge `key`, or None if only the device can tell"""
         first = self.edges.get(key)
         if first is None:
-            first = int(full_scan())
+            first = int(full_scan())     # (the caller counts the launch: a candidate batch may answer without one)
             if len(self.edges) >= self.max_edges:
                 self.edges.clear()
             self.edges[key] = first
-            self.stats["edge_launches"] += 1
         else:
             self.stats["edge_hits"] += 1
         hi = N if n_max is None else min(n_max, N)
@@ -330,6 +422,9 @@ if HAVE_REFERENCE:
             self._slot = None
             self._mask_cache: Dict[tuple, tuple] = {}
             self._slot_by_mode: Dict[Optional[int], int] = {}
+            self._last_edge_end: Optional[bytes] = None      # end configuration of the last edge found free (candidate speculation)
+            self.max_candidate_edges = 2048
+            self.query_stats = {"configs": 0, "robot": 0, "edges": 0, "paths": 0}   # what the planner asked, cached or not
             super().__init__()
             self.spec = ProblemSpec(agent_type=AgentType.MULTI_AGENT, constraints=ConstraintType.UNCONSTRAINED,
                                     manipulation=ManipulationType.MANIPULATION, dependency=DependencyType.FULLY_ORDERED,
@@ -351,7 +446,61 @@ if HAVE_REFERENCE:
             return config_cost(start, end, self.cost_metric, self.cost_reduction)
 
         def batch_config_cost(self, starts, ends, tmp_agent_slice=None):
-            return batch_config_cost(starts, ends, self.cost_metric, self.cost_reduction, tmp_agent_slice=tmp_agent_slice)
+            costs = batch_config_cost(starts, ends, self.cost_metric, self.cost_reduction, tmp_agent_slice=tmp_agent_slice)
+            # candidate-edge speculation (SpeculativeCache): the PRM search asks for the edge costs from the node it has
+            # just reached to all of its neighbours (prm_graph.py:706-712) -- those are the edges it may check next
+            if (self.spec_cache is not None and self._last_edge_end is not None and tmp_agent_slice is None
+                    and isinstance(ends, np.ndarray) and ends.ndim == 2 and len(ends) >= 2 and hasattr(starts, "state")):
+                q1 = starts.state()
+                if q1.tobytes() == self._last_edge_end:
+                    self._prefetch_candidates(q1, ends, costs)
+            return costs
+
+        def _prefetch_candidates(self, q1: np.ndarray, ends: np.ndarray, costs: np.ndarray) -> None:
+            dev = self.model.device
+            submit = getattr(dev, "prefetch_edges", None)
+            if submit is None or self._slot is None:
+                return
+            key = q1.tobytes()
+            for old in self.spec_cache.candidates.get(key, ()):
+                if old.slot == self._slot and old.q2.shape == ends.shape and np.array_equal(old.q2, ends):
+                    return                               # same node expanded again in the same search state
+            if len(ends) > self.max_candidate_edges:     # cheapest edges first
+                keep = np.argpartition(costs, self.max_candidate_edges)[: self.max_candidate_edges]
+                ends = ends[keep]
+            q2 = np.ascontiguousarray(ends, np.float64)
+            # N exactly like is_edge_collision_free: max(2, int(|dq|_inf / resolution) + 1) in fp64
+            N = np.maximum((np.max(np.abs(q2 - q1[None, :]), axis=1) / self.collision_resolution).astype(np.int64) + 1, 2).astype(np.int32)
+            params = (float(self.collision_resolution), False, None)
+            ticket = submit(self._slot, q1.astype(np.float32), q2.astype(np.float32), self.collision_resolution, N=N)
+            self.spec_cache.add_candidates(key, SpeculativeCache.Candidates(self._slot, q2, N, params, ticket))
+
+        def _candidate_first(self, q1_bytes: bytes, q2: np.ndarray, N: int, params: tuple) -> Optional[int]:
+            """first colliding position of edge (q1, q2) if it is one of q1's speculated candidate edges, else None"""
+            cand, i = None, None
+            q2_bytes = q2.tobytes()
+            for c in self.spec_cache.candidates.get(q1_bytes, ()):
+                if c.params != params:
+                    continue
+                j = c.row_of(q2_bytes)
+                if j is not None and int(c.N[j]) == N:
+                    if cand is None or (c.slot == self._slot and cand.slot != self._slot):
+                        cand, i = c, j
+            if cand is None:
+                return None
+            dev = self.model.device
+            if cand.slot != self._slot:      # speculated for another kinematic tree (transition twin): redo the batch here
+                q1 = np.frombuffer(q1_bytes, np.float64)
+                free, first = dev.check_edges(self._slot, np.repeat(q1[None].astype(np.float32), len(cand.N), 0),
+                                              cand.q2.astype(np.float32), params[0], N=cand.N)
+                cand.first = np.array(CudaDevice.to_numpy(first), np.int32)
+                cand.slot, cand.ticket = self._slot, None
+                self.spec_cache.stats["candidate_reissues"] += 1
+            elif cand.first is None:
+                _, first = dev.collect_edges(cand.ticket, len(cand.N))
+                cand.first = np.asarray(first, np.int32)
+            self.spec_cache.stats["candidate_hits"] += 1
+            return int(cand.first[i])
 
         # ---- modes -------------------------------------------------------------------------
         def _relinks_for_mode(self, m: "Mode") -> List[Tuple[str, str, np.ndarray]]:
@@ -419,12 +568,15 @@ if HAVE_REFERENCE:
                 if self.spec_cache is not None:
                     self.spec_cache.new_block(batch)
                 for i in range(batch_size):
+                    if self.spec_cache is not None:
+                        self.spec_cache.cursor = i
                     yield self.start_pos.from_flat(batch[i])
 
         # ---- collision queries -------------------------------------------------------------
         def is_collision_free(self, q, m, collision_tolerance: Optional[float] = None) -> bool:
             if q is None:
                 raise ValueError
+            self.query_stats["configs"] += 1
             self.set_to_mode(m)
             if self.spec_cache is not None and collision_tolerance is None:
                 slot = self._slot
@@ -451,6 +603,7 @@ if HAVE_REFERENCE:
             return CudaDevice.to_numpy(free), CudaDevice.to_numpy(first)
 
         def is_collision_free_np(self, q, m, collision_tolerance=None, set_mode: bool = True) -> bool:
+            self.query_stats["configs"] += 1
             if set_mode:
                 self.set_to_mode(m)
             return self._one_config(np.asarray(q, np.float32)[None], collision_tolerance)
@@ -476,6 +629,7 @@ if HAVE_REFERENCE:
             penetrating pair involves robot r (or a frame of its task) and no other robot."""
             if isinstance(r, str):
                 r = [r]
+            self.query_stats["robot"] += 1
             if set_mode:
                 self.set_to_mode(m)
             rel, oth = self._robot_masks(list(r), m)
@@ -491,19 +645,38 @@ if HAVE_REFERENCE:
                 N = max(2, int(config_dist(q1, q2, "max") / resolution) + 1)
             if N_start > N:
                 assert False
+            self.query_stats["edges"] += 1
+            s1, s2 = q1.state(), q2.state()
+            whole = N_start == 0 and (N_max is None or N_max >= N)
+            if N <= 2 and not include_endpoints:   # no interior sample (rai_base_env.py:655-674 loops over nothing): free
+                if whole:
+                    self._last_edge_end = s2.tobytes()
+                return True
             self.set_to_mode(m)
-            a, b = np.asarray(q1.state(), np.float32)[None], np.asarray(q2.state(), np.float32)[None]
+            a, b = np.asarray(s1, np.float32)[None], np.asarray(s2, np.float32)[None]
             Ns = np.array([N], np.int32)
             if self.spec_cache is not None:
                 slot = self._slot
-                key = (slot, q1.state().tobytes(), q2.state().tobytes(), int(N), float(resolution), bool(include_endpoints),
-                       None if tolerance is None else float(tolerance))
-                hit = self.spec_cache.edge_window(key, N_start, N_max, int(N), lambda: self._edges(
-                    a, b, resolution, N=Ns, include_endpoints=include_endpoints, tol=tolerance)[1][0])
+                tol_key = None if tolerance is None or tolerance == self.collision_tolerance else float(tolerance)
+                b1 = s1.tobytes()
+                key = (slot, b1, s2.tobytes(), int(N), float(resolution), bool(include_endpoints), tol_key)
+
+                def full_scan():
+                    p0 = self._candidate_first(b1, s2, int(N), (float(resolution), bool(include_endpoints), tol_key))
+                    if p0 is not None:
+                        return p0
+                    self.spec_cache.stats["edge_launches"] += 1
+                    return self._edges(a, b, resolution, N=Ns, include_endpoints=include_endpoints, tol=tolerance)[1][0]
+
+                hit = self.spec_cache.edge_window(key, N_start, N_max, int(N), full_scan)
                 if hit is not None:
+                    if hit and whole:
+                        self._last_edge_end = s2.tobytes()
                     return hit
             free, _ = self._edges(a, b, resolution, N=Ns, n_start=N_start, n_max=N_max, include_endpoints=include_endpoints,
                                   tol=tolerance)
+            if free[0] and whole:
+                self._last_edge_end = s2.tobytes()
             return bool(free[0])
 
         def is_path_collision_free(self, path, binary_order: bool = True, resolution=None, tolerance=None,
@@ -512,6 +685,7 @@ if HAVE_REFERENCE:
             the interior of every edge collision free -- from one vertex batch and one edge batch per mode."""
             if resolution is None:
                 resolution = self.collision_resolution
+            self.query_stats["paths"] += 1
             L = len(path)
             by_mode: Dict[int, list] = {}
             for i, st in enumerate(path):
@@ -752,6 +926,8 @@ if HAVE_REFERENCE:
                 if self.spec_cache is not None:
                     self.spec_cache.new_block(batch)
                 for i in range(batch_size):
+                    if self.spec_cache is not None:
+                        self.spec_cache.cursor = i
                     yield self.start_pos.from_flat(batch[i])
 
         @property
@@ -783,8 +959,12 @@ if HAVE_REFERENCE:
             Ns = np.array([N], np.int32)
             if self.spec_cache is not None:  # (the abstract env ignores `tolerance`, abstract_env.py:301-354)
                 key = (0, q1.state().tobytes(), q2.state().tobytes(), int(N), float(resolution), bool(include_endpoints))
-                hit = self.spec_cache.edge_window(key, N_start, N_max, int(N), lambda: self.device.check_edges(
-                    q1.state()[None], q2.state()[None], resolution, N=Ns, include_endpoints=include_endpoints)[1][0])
+                def full_scan():
+                    self.spec_cache.stats["edge_launches"] += 1
+                    return self.device.check_edges(q1.state()[None], q2.state()[None], resolution, N=Ns,
+                                                   include_endpoints=include_endpoints)[1][0]
+
+                hit = self.spec_cache.edge_window(key, N_start, N_max, int(N), full_scan)
                 if hit is not None:
                     return hit
             f, _ = self.device.check_edges(q1.state()[None], q2.state()[None], resolution, N=Ns,

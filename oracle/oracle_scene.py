@@ -62,7 +62,13 @@ def _f64(a):
 
 
 def max_threads() -> int:
-    return int(lib().orc_max_threads())
+    """host cores this process may use.  NOT omp_get_max_threads(): launchers such as torch.distributed.run export
+    OMP_NUM_THREADS=1, which silently turned the "all host threads" CPU baseline into a single-thread one; every
+    oracle entry point passes its thread count explicitly (`num_threads` clause), so the environment cannot override it."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def check_configs(blob64: np.ndarray, q, tol: float = -1.0, rel=None, oth=None, nthreads: int = 1):

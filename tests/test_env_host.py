@@ -277,3 +277,48 @@ def test_reference_informed_tree_planners_solve_b200_handover(reference, envmod,
     assert path is not None and env.is_valid_plan(path) and env.is_terminal_mode(path[-1].mode)
     assert len({tuple(s.mode.task_ids) for s in path}) == 6
     assert dev.calls["robot"] > 0 and dev.calls["edges"] > 0
+
+
+def test_candidate_edge_and_pinned_sample_speculation_change_no_answer(reference, envmod):
+    """a PRM node's candidate edges go to the device in one asynchronous batch at expansion time
+    (env.batch_config_cost names them), pinned transition samples are validated by the block; the reference's PRM
+    takes exactly the same decisions and makes several times fewer device round trips than queries."""
+    from oracle.oracle_device import OraclePrefetchDevice
+    runs = {}
+    for kind in ("plain", "speculative"):
+        dev = OraclePrefetchDevice(nthreads=4) if kind == "speculative" else OracleSceneDevice(nthreads=4)
+        env = envmod.b200_box_rearrangement(device=dev, speculate=kind == "speculative")
+        before = dict(dev.calls)          # (the keyframe solver of the constructor used the device too)
+        path, _ = run_planner(env, "prm", 2, max_time=300)
+        assert path is not None
+        calls = {k: v - before.get(k, 0) for k, v in dev.calls.items()}
+        runs[kind] = (np.stack([s.q.state() for s in path]), calls, dict(env.query_stats),
+                      None if env.spec_cache is None else dict(env.spec_cache.stats))
+    pa, pb = runs["plain"][0], runs["speculative"][0]
+    assert pa.shape == pb.shape and np.array_equal(pa, pb)
+    calls_plain, calls_spec, queries, stats = runs["plain"][1], runs["speculative"][1], runs["speculative"][2], runs["speculative"][3]
+    print("round trips plain / speculative:", calls_plain, calls_spec, "queries:", queries, stats)
+    assert stats["candidate_hits"] > 0 and stats["pinned_hits"] > 0
+    # (most round trips of this easy problem belong to the shortcutter's 250 path checks, one vertex and one edge batch
+    # per mode of the path; the single-edge launches of the search are what the candidate batches remove)
+    assert sum(calls_spec.values()) < sum(calls_plain.values())
+    assert calls_spec["edges"] + calls_spec["prefetch"] < calls_plain["edges"]
+    # single-edge launches nearly vanish: the candidate batches answer them
+    assert stats["edge_launches"] * 5 < queries["edges"]
+
+
+def test_path_check_vertex_rules_follow_the_reference(reference, envmod):
+    """advisor r1: which vertices the reference checks depends on check_edges_in_order / check_start_and_end
+    (planning_env.py:1791-1878); a colliding first or last vertex must be seen exactly when the reference sees it."""
+    from multi_robot_multi_goal_planning.problems.planning_env import BaseProblem, State
+    env = envmod.b200_two_dim_handover(device=OracleSceneDevice(), speculate=False)
+    m = env.start_mode
+    free = env.start_pos.state().copy()
+    bad = free.copy()
+    bad[:2] = [0.4, 1.0]                       # a1 inside obs2
+    near = free + 0.003                        # sub-resolution moves: no interior samples, only vertices matter
+    for pts in ([bad, free, near], [free, near, bad], [free, bad + 0.0, free]):
+        path = [State(env.start_pos.from_flat(np.array(p)), m) for p in pts]
+        for kw in ({}, {"check_edges_in_order": True}, {"check_start_and_end": False},
+                   {"check_edges_in_order": True, "check_start_and_end": False}):
+            assert env.is_path_collision_free(path, **kw) == BaseProblem.is_path_collision_free(env, path, **kw), (pts, kw)

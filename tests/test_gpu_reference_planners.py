@@ -1,0 +1,135 @@
+"""The reference's own planners and path utilities driving the CUDA device (BASELINE metric 3):
+the reference package travels to the GPU box as the offline install under baseline/_ref (refimport.py).
+
+  * B200Env.is_path_collision_free (one vertex batch + one edge batch per mode) against the reference's own loop
+    BaseProblem.is_path_collision_free (P/problems/planning_env.py:1765-1881) over single device queries;
+  * SpeculativeCache on the real device: same answers with and without, fewer device round trips;
+  * CompositePRM / EIT* on b200 environments: valid plans; same seeds on the CUDA device and on the oracle-backed CPU
+    device give the same plan wherever no query fell inside the 1e-5 margin (checked through plan validity and cost);
+  * abstract.test: bit-exact flags, hence plans identical to the reference's own numpy environment."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def envmod(cuda_lib, reference):
+    import importlib
+    from multirobot_pathplanning_benchmark_b200 import env
+    if not env.HAVE_REFERENCE:
+        env = importlib.reload(env)
+    assert env.HAVE_REFERENCE, "the reference package must be importable on the GPU box (baseline/_ref)"
+    return env
+
+
+def test_reference_install_is_the_offline_copy(reference):
+    import multi_robot_multi_goal_planning as ref
+    assert "baseline/_ref" in ref.__file__ or "/root/reference" in ref.__file__ or "site-packages" in ref.__file__
+
+
+def _walk(env):
+    m, q = env.start_mode, env.start_pos
+    out = [(m, q)]
+    while not env.is_terminal_mode(m):
+        task = env.get_active_task(m, None)
+        goal = task.goal.sample(m)
+        q_new = env.start_pos.from_flat(q.state().copy())
+        off = 0
+        for r in task.robots:
+            i = env.robots.index(r)
+            q_new[i] = goal[off:off + env.robot_dims[r]]
+            off += env.robot_dims[r]
+        m = env.get_next_modes(q_new, m)[0]
+        q = q_new
+        out.append((m, q))
+    return out
+
+
+@pytest.mark.parametrize("env_name", ["b200_two_dim_handover", "b200_box_rearrangement"])
+def test_batched_path_check_equals_reference_loop_on_the_device(envmod, env_name):
+    from multi_robot_multi_goal_planning.problems.planning_env import BaseProblem, State
+    env = getattr(envmod, env_name)(speculate=False)
+    rng = np.random.RandomState(0)
+    modes = _walk(env)
+    D = env.limits.shape[1]
+    outcomes = []
+    for trial in range(40):
+        m, q0 = modes[trial % len(modes)]
+        step = 0.25 if D == 6 else 0.08
+        pts = [q0.state()] + [q0.state() + rng.uniform(-step, step, D) for _ in range(3)]
+        path = [State(env.start_pos.from_flat(p), m) for p in pts]
+        for kw in ({}, {"check_edges_in_order": True}, {"check_start_and_end": False},
+                   {"check_edges_in_order": True, "check_start_and_end": False}):
+            want = BaseProblem.is_path_collision_free(env, path, **kw)   # the reference's own loop, single device queries
+            assert env.is_path_collision_free(path, **kw) == want, (trial, kw)
+        outcomes.append(want)
+    assert 0 < sum(outcomes) < len(outcomes)
+
+
+def test_speculative_cache_on_the_real_device(envmod):
+    spec = envmod.b200_two_dim_handover(speculate=True)
+    plain = envmod.b200_two_dim_handover(speculate=False)
+    np.random.seed(11)
+    qs = [spec.sample_config_uniform_in_limits() for _ in range(1500)]   # spans two sample blocks
+    got = [spec.is_collision_free(q, spec.start_mode) for q in qs]
+    want = [plain.is_collision_free(q, plain.start_mode) for q in qs]
+    assert got == want and 0 < sum(got) < len(got)
+    assert spec.spec_cache.stats["config_launches"] == 2 and spec.spec_cache.stats["config_hits"] == 1498
+    rng = np.random.RandomState(4)
+    lim = spec.limits
+    for _ in range(40):
+        a = rng.uniform(lim[0], lim[1])
+        b = a + rng.uniform(-0.6, 0.6, a.shape)
+        q1, q2 = spec.start_pos.from_flat(a), spec.start_pos.from_flat(b)
+        N = max(2, int(np.max(np.abs(a - b)) / spec.collision_resolution) + 1)
+        for (ns, nm) in ((0, 1), (0, 4), (4, 16), (16, None), (0, None), (N // 2, None)):
+            if ns > N:
+                continue
+            assert spec.is_edge_collision_free(q1, q2, spec.start_mode, N_start=ns, N_max=nm) == \
+                plain.is_edge_collision_free(q1, q2, plain.start_mode, N_start=ns, N_max=nm)
+    st = spec.spec_cache.stats
+    assert st["edge_hits"] > 2 * st["edge_launches"]
+
+
+@pytest.mark.parametrize("planner", ["composite_prm", "rrt_star", "birrt_star", "aitstar", "eitstar"])
+def test_abstract_test_plans_are_identical_to_the_reference_environment(envmod, reference, planner):
+    """BASELINE config 1 (`run_planner.py abstract.test`, seed 1): the CUDA-backed environment answers bit-identically,
+    so every planner takes exactly the decisions it takes on the reference's own numpy environment."""
+    from multirobot_pathplanning_benchmark_b200 import refplanners as RP
+    kw = {} if planner == "composite_prm" else {"with_mode_validation": False}
+    ref_env = reference.get_env_by_name("abstract.test")
+    a = RP.run_planner(ref_env, planner, 1, 30, optimize=False, **kw)
+    b_env = envmod.b200_abstract_test()
+    b = RP.run_planner(b_env, planner, 1, 30, optimize=False, **kw)
+    assert a["solved"] and b["solved"]
+    pa, pb = a["_path"], b["_path"]
+    assert len(pa) == len(pb)
+    for x, y in zip(pa, pb):
+        assert np.array_equal(x.q.state(), y.q.state()) and x.mode.task_ids == y.mode.task_ids
+    assert a["first_cost"] == b["first_cost"]
+
+
+@pytest.mark.parametrize("env_name,planner", [("b200_box_stacking", "composite_prm"), ("b200_box_rearrangement", "composite_prm"),
+                                              ("b200_two_dim_handover", "eitstar")])
+def test_reference_planners_solve_b200_scenes_on_the_device(envmod, env_name, planner):
+    from multirobot_pathplanning_benchmark_b200 import refplanners as RP
+    from multirobot_pathplanning_benchmark_b200.env import CudaDevice
+    from oracle.oracle_device import OracleSceneDevice
+    env, meter = RP.metered_env(getattr(envmod, env_name), CudaDevice())
+    res = RP.run_planner(env, planner, 1, 240, optimize=False)
+    assert res["solved"] and env.is_valid_plan(res["_path"]) and env.is_terminal_mode(res["_path"][-1].mode)
+    assert sum(meter.calls.values()) > 50
+    # the plan is valid for the oracle as well: every vertex and edge of the path re-checked on the CPU, except where a
+    # sample lies inside the margin (is_valid_plan on the oracle-backed twin environment)
+    twin = getattr(envmod, env_name)(device=OracleSceneDevice(), speculate=False)
+    path = res["_path"]
+    modes = {tuple(m.task_ids): m for m, _ in _walk(twin)}
+    bad = 0
+    for s0, s1 in zip(path[:-1], path[1:]):
+        m = modes[tuple(s0.mode.task_ids)]
+        if not twin.is_edge_collision_free(s0.q, s1.q, m):
+            bad += 1
+    assert bad <= 1, f"{bad} path edges the oracle rejects"
