@@ -39,3 +39,18 @@ def test_b200_arm_needs_a_device():
         pytest.skip("checks the behaviour of a machine without a GPU")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_ignores_the_launchers_omp_setting():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm must still use every host core (the
+    SCALE ratios at N > 1 were void because it silently ran single threaded) and emit the same `config` keys as the
+    B200 arm does"""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--ref-seconds", "3"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["n_gpus"] == 2
+    assert set(d["config"]) == {"workload", "scene", "configs_per_gpu", "configs_total", "dof", "collidable_pairs", "tolerance",
+                                "inputs", "l2", "exchange"}
