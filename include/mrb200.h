@@ -116,7 +116,8 @@ int mrb200_query_edges_host(mrb200_scene_t* scene, int slot, const float* q1_hos
  * named them all).  submit: inputs are copied into a pinned buffer owned by the handle, H2D + kernel + D2H are queued on
  * `stream`, an event is recorded and the call returns with a ticket.  q1_host holds q1_rows = 1 (one start for all edges)
  * or E rows.  Whole edges only (no window).  collect: waits for the ticket's event, writes free_host[E] and
- * first_pos_host[E] (nullable).  A ticket expires after 8 further submits on the handle. */
+ * first_pos_host[E] (nullable).  A ticket expires after 64 further submits on the handle
+ * (collect then fails with MRB200_ERR_ARG and the caller re-submits). */
 int mrb200_submit_edges_host(mrb200_scene_t* scene, int slot, const float* q1_host, int q1_rows, const float* q2_host,
                              int64_t E, double resolution, const int32_t* N_host, int include_endpoints, float tol,
                              int64_t* ticket_out, mrb200_stream_t stream);
@@ -159,6 +160,10 @@ int mrb200_batch_cost(const double* a_dev, int a_is_single, const double* b_dev 
  * mode: 0 = automatic, 1 = exact fp64 CUDA-core path, 2 = tensor-core candidates + fp64 re-rank
  * (euclidean / max_euclidean only); both return the same indices. */
 size_t mrb200_knn_workspace_bytes(int64_t Q, int64_t N, int D, int k);
+/* byte offset, inside the workspace of the last tensor-core mrb200_knn call with these sizes, of two uint32 statistics:
+ * [0] bit pattern of the largest squared slice norm (the error bound's scale), [1] rows the re-rank could not certify
+ * (recomputed by the exact kernel inside the same call).  Read after synchronising the stream. */
+size_t mrb200_knn_stats_offset(int64_t Q, int64_t N, int D, int k);
 int mrb200_knn(const double* queries_dev /*[Q, D]*/, const double* corpus_dev /*[N, D]*/, int64_t Q, int64_t N,
                int D, const int32_t* slices_host, int R, int metric, int k, int32_t* out_idx_dev /*[Q, k]*/,
                double* out_dist_dev /*[Q, k]*/, void* workspace_dev, size_t workspace_bytes, int mode,

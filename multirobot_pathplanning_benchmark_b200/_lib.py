@@ -50,6 +50,7 @@ SIGNATURES = {
     "mrb200_batch_cost": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, C.c_double, c_vp,
                                     c_vp]),
     "mrb200_knn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "mrb200_knn_stats_offset": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "mrb200_knn": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp,
                              C.c_size_t, C.c_int, c_vp]),
     "mrb200_radius_splits": (C.c_int, [C.c_int64, C.c_int64]),

@@ -65,7 +65,7 @@ struct mrb200_scene {
         int64_t E = 0, seq = -1;
         bool pending = false;
     };
-    static constexpr int N_TICKETS = 8;
+    static constexpr int N_TICKETS = 64;
     EdgeTicket tickets[N_TICKETS];
     int64_t ticket_seq = 0;
     int* stats_dev = nullptr;   // [2 * slots] (configurations seen, decided in phase A) per mode slot
@@ -688,15 +688,10 @@ int mrb200_batch_dist(const double* q, const double* pts, int64_t N, int D, cons
     return MRB200_OK;
 }
 
-// candidates kept per row by the tensor-core path
-static int tc_candidates(int k) { return k + 8; }
-
 static bool tc_usable(int64_t Q, int64_t N, int D, const mrb::Slices& sl, int metric, int k, mrb::TcPlan* plan) {
-    if (k > 48 || N < 1024 || Q < 1) return false;
+    if (k > mrb::knn_tc_max_k() || N < 1024 || Q < 1) return false;
     if (!mrb::knn_tc_make_plan(D, sl, metric, plan)) return false;
-    // narrower corpus tiles until query tile + corpus stages + candidate heaps fit in shared memory
-    while (plan->tn > 32 && mrb::knn_tc_smem_bytes(*plan, tc_candidates(k)) > 224 * 1024) plan->tn >>= 1;
-    return mrb::knn_tc_smem_bytes(*plan, tc_candidates(k)) <= 224 * 1024;
+    return mrb::knn_tc_smem_bytes(*plan, 0) <= 224 * 1024;
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -714,25 +709,32 @@ int mrb200_batch_cost(const double* a, int a_is_single, const double* b, int64_t
     return MRB200_OK;
 }
 
+static int tc_max_splits(int64_t Q) {   // upper bound of knn_tc_splits for any corpus
+    const int64_t qt = (Q + 127) / 128;
+    int64_t s = (160 + qt - 1) / qt;
+    return (int)(s > 32 ? 32 : s < 1 ? 1 : s);
+}
+
+static size_t tc_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
+    // sized for the worst plan: K steps of the euclidean plan + one per robot (<= 8 accumulators), the narrowest tile
+    const int ks = (D + 2 + 7) / 8 + 8;
+    const int splits = tc_max_splits(Q);
+    const size_t lists = (size_t)splits * 2;
+    return 256 + align256((size_t)((Q + 127) / 128) * ks * 128 * 32) + align256((size_t)(N + 256) * ks * 32) +
+           align256(lists * (size_t)Q * ((size_t)(k + 16) * 8 + 4)) + align256((size_t)Q) + 4096;
+}
+
 size_t mrb200_knn_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
     if (Q <= 0 || k <= 0) return 256;
     const int splits = mrb::knn_pick_splits(Q, N);
-    size_t exact = align256((size_t)splits * (size_t)Q * (size_t)k * 12 + 256);
-    // the tensor-core path needs its operands, candidate lists and certification flags as well; size for
-    // the worst plan (one accumulator per dimension pair is never worse than 8 accumulators of 32 columns)
-    mrb::Slices sl{};
-    mrb::TcPlan plan;
-    size_t tc = 0;
-    if (mrb::knn_tc_make_plan(D, sl, MRB200_METRIC_EUCLIDEAN, &plan)) {
-        // euclidean has the largest K padding; max_euclidean plans use at most the same K steps + 1 per robot
-        mrb::TcPlan worst = plan;
-        worst.KS = plan.KS + mrb::KNN_MAX_R;
-        worst.tn = 256;
-        const int64_t ct = (N + 31) / 32;  // smallest tile width -> most tiles
-        tc = align256((size_t)((Q + 127) / 128) * worst.KS * 128 * 32) + align256((size_t)ct * worst.KS * 32 * 32) +
-             align256((size_t)64 * (Q + 128) * tc_candidates(k) * 8) + align256((size_t)Q) + 4096;
-    }
-    return exact + tc;
+    const size_t exact = align256((size_t)splits * (size_t)Q * (size_t)k * 12 + 256);
+    return exact + (k <= mrb::knn_tc_max_k() ? tc_workspace_bytes(Q, N, D, k) : 0);
+}
+
+size_t mrb200_knn_stats_offset(int64_t Q, int64_t N, int D, int k) {
+    if (Q <= 0 || k <= 0) return 0;
+    const int splits = mrb::knn_pick_splits(Q, N);
+    return align256((size_t)splits * (size_t)Q * (size_t)k * 12 + 256) + align256((size_t)Q);
 }
 
 int mrb200_knn(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const int32_t* slices_host, int R, int metric,
@@ -750,13 +752,14 @@ int mrb200_knn(const double* queries, const double* corpus, int64_t Q, int64_t N
     unsigned char* tc_ws = (unsigned char*)workspace + align256((size_t)splits * (size_t)Q * (size_t)k * 12 + 256);
     mrb::TcPlan plan;
     const bool tc_ok = tc_usable(Q, N, D, sl, metric, k, &plan);
-    if (mode == 2 && !tc_ok) return fail(MRB200_ERR_ARG, "knn: the tensor-core path needs metric euclidean / max_euclidean, k <= 48, N >= 1024");
+    if (mode == 2 && !tc_ok)
+        return fail(MRB200_ERR_ARG, "knn: the tensor-core path needs metric euclidean / max_euclidean, k <= %d, N >= 1024", mrb::knn_tc_max_k());
     const bool use_tc = mode == 2 || (mode == 0 && tc_ok && Q >= 256 && N >= 4096);
     const uint8_t* skip = nullptr;
     if (use_tc) {
-        const int kc = tc_candidates(k);
         const int64_t ct = (N + plan.tn - 1) / plan.tn;
         const int tsplits = mrb::knn_tc_splits(Q, ct);
+        const int kc = mrb::knn_tc_slots(k, 2 * tsplits);   // output slots per row and list
         uint8_t* certified = tc_ws;
         cudaError_t e = mrb::launch_knn_tc(queries, corpus, Q, N, D, sl, metric, k, kc, plan, tsplits, tc_ws + align256((size_t)Q), out_idx,
                                            out_dist, certified, st);

@@ -81,6 +81,9 @@ struct TcPlan;
 bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan);
 size_t knn_tc_smem_bytes(const TcPlan& plan, int kc);
 int knn_tc_splits(int64_t Q, int64_t n_ctiles);
+int knn_tc_keep(int k, int n_lists);    // candidates a list keeps at least
+int knn_tc_slots(int k, int n_lists);   // output slots per row and list
+int knn_tc_max_k();
 size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, int splits);
 cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
                           int k, int kc, const TcPlan& plan, int splits, void* workspace, int32_t* out_idx, double* out_dist,

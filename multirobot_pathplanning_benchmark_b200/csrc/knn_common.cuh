@@ -31,6 +31,7 @@ struct TcPlan {
     int ksteps[KNN_MAX_R];
     int KS;                  // total K steps
     int tn;                  // corpus columns per accumulator tile (UMMA N)
+    int stages;              // shared-memory stages of corpus tiles (2..4)
 };
 
 // distance between q (registers / local) and p (any memory), fp64, reference operand order:

@@ -4,21 +4,25 @@
 // (P/planners/prm/prm_graph.py:407-447, distances P/problems/core/configuration.py:303-329) for
 // whole query batches.
 //
-// Per robot slice the squared distance is a dense contraction of augmented vectors
-//   A-row (query):  [ q_hi  q_hi  q_lo | |q|^2_hi |q|^2_lo 1 1 | 0.. ]
-//   B-row (corpus): [-2c_hi -2c_lo -2c_hi | 1 1 |c|^2_hi |c|^2_lo | 0.. ]
-// where x_hi = tf32(x), x_lo = tf32(x - x_hi) (3xTF32 split, every entry exactly representable in
-// TF32).  knn_tc_prep_kernel writes both operands in the UMMA canonical K-major, no-swizzle
-// layout (8-row x 16-byte core matrices; LBO = 128 B between the two K halves of an instruction,
-// SBO = 256 B between 8-row groups), tile after tile, so a whole operand tile is ONE contiguous
-// bulk copy.  knn_tc_kernel: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (M = 128 query
-// rows, N = corpus columns per accumulator, K = 8 per instruction, kind::tf32, FP32 accumulators
-// in TMEM, one accumulator per robot, double buffered), warp 2 = TMEM allocator, warps 4-7 =
-// epilogue: tcgen05.ld of 32 columns per robot, max over robots, per-row bounded heap of
-// k + slack candidates in shared memory.  knn_rerank_kernel recomputes the candidates' distances
-// in fp64 with the reference's operand order, sorts by (distance, index) and certifies each row:
-// if the exact k-th squared distance is not below (smallest discarded coarse value - error bound)
-// the row is flagged and the caller recomputes it with the exact kernel (knn_kernels.cu).
+// Per robot slice the squared distance is a dense contraction of augmented vectors, rounded ONCE to TF32:
+//   A-row (query):  [  q_1 ..  q_d | |q|^2 | 1     | 0.. ]
+//   B-row (corpus): [-2c_1 .. -2c_d | 1     | |c|^2 | 0.. ]        (K = d + 2 -> one K step of 8 for a 6-dof arm)
+// The coarse value carries an absolute error of at most (2^-9 + 2^-10) * max squared slice norm (input rounding;
+// products of TF32 numbers are exact in the FP32 accumulator), which the certification below accounts for -- round 1
+// used a 3xTF32 split (three times the MMAs) to make the coarse value nearly exact, which the re-rank never needed.
+// knn_tc_prep_kernel writes the corpus operand in the UMMA canonical K-major, no-swizzle layout (8-row x 16-byte core
+// matrices; LBO = 128 B between the two K halves of an instruction, SBO = 256 B between 8-row groups), tile after tile,
+// so a whole operand tile is ONE contiguous bulk copy; the query operand is plain row-major and lives in TENSOR MEMORY
+// for the life of the CTA (tcgen05.st once, then every MMA reads A from TMEM: shared memory only feeds the small B tile).
+// knn_tc_kernel: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (M = 128 query rows, N = corpus columns per
+// accumulator, K = 8 per instruction, kind::tf32, FP32 accumulators in TMEM, one accumulator per robot, double
+// buffered), warp 2 = TMEM allocator, warps 4-11 = epilogue: tcgen05.ld of 16 columns per robot, max over robots, a min
+// tree + warp vote that skips chunks without a candidate, else THRESHOLD-FIRST selection: values below the thread's
+// current threshold are appended to its list in shared memory (no ordering); when a list fills up, the warp bisects
+// for the value that keeps about `m` entries, drops the rest and lowers the threshold.  knn_rerank_kernel recomputes the
+// candidates' distances in fp64 with the reference's operand order, sorts by (distance, index) and certifies each
+// row: if the exact k-th squared distance is not below (smallest discard threshold - error bound) the row is flagged
+// and the caller recomputes it with the exact kernel (knn_kernels.cu).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,11 +33,14 @@
 namespace mrb {
 
 constexpr int TC_TM = 128;        // query rows per CTA (UMMA M)
-constexpr int TC_STAGES = 3;      // shared-memory stages of corpus tiles
+constexpr int TC_STAGES = 4;      // shared-memory stages of corpus tiles, at most (TcPlan::stages)
 constexpr int TC_THREADS = 384;   // warps 0-3: producer / MMA / TMEM allocator / spare, warps 4-11: epilogue
-constexpr int TC_STG = 8;         // staged candidates per epilogue thread between batched heap updates
+constexpr int TC_LIST = 80;       // candidate list entries per epilogue thread (row x column half)
+constexpr int TC_TRIG = TC_LIST - 16;   // a 16-column chunk can add 16 entries: compact above this fill
+constexpr int TC_SLACK = 8;       // a compaction keeps between m and m + TC_SLACK entries
 constexpr float TC_BIG = 1.0e30f;
 constexpr int TC_MAX_KS = 40;     // knn_tc_make_plan accepts plans up to this many K steps
+constexpr unsigned TC_FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM primitives
@@ -48,15 +55,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, both K-major, TF32 in, FP32 out
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]^T: A = 128 lanes x 8 TF32 columns of tensor memory, B K-major in shared memory, FP32 out
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n"
         "}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
 }
 // arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed
@@ -65,20 +72,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 consecutive FP32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
 }
 // 16 consecutive FP32 columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -92,6 +85,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 8 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor: K-major, no swizzle, LBO = 128 B, SBO = 256 B, version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc(const void* smem) {
@@ -109,18 +110,25 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// monotone map float -> unsigned (finite floats): bisection over candidate keys works on these
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
 // ---------------------------------------------------------------------------------------------
 // operand layout
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline int64_t tc_elem_offset(int rows_per_tile, int KS, int64_t row, int kglob) {
-    // float index of element (row, kglob) of an operand stored tile after tile, K step after K step
+    // float index of element (row, kglob) of the corpus operand, stored tile after tile, K step after K step
     const int64_t tile = row / rows_per_tile;
     const int m = (int)(row - tile * rows_per_tile);
     const int ks = kglob >> 3, k = kglob & 7;
     return (tile * KS + ks) * (int64_t)rows_per_tile * 8 + (m >> 3) * 64 + (k >> 2) * 32 + (m & 7) * 4 + (k & 3);
 }
 
-// one thread per (padded) row; side 0 = queries (A), 1 = corpus (B)
+// one thread per (padded) row; side 0 = queries (A, row-major [n_pad][8 KS]), 1 = corpus (B, UMMA tile layout)
 __global__ void __launch_bounds__(128) knn_tc_prep_kernel(const double* __restrict__ X, int64_t n, int64_t n_pad, int D,
                                                           const __grid_constant__ TcPlan plan, int side, int rows_per_tile,
                                                           float* __restrict__ out, unsigned* __restrict__ max_norm_bits) {
@@ -128,28 +136,26 @@ __global__ void __launch_bounds__(128) knn_tc_prep_kernel(const double* __restri
     if (row >= n_pad) return;
     const bool real = row < n;
     float worst = 0.f;
+    const int KW = plan.KS * 8;
+    auto put = [&](int kglob, float v) {
+        if (side == 0) out[row * KW + kglob] = v;
+        else out[tc_elem_offset(rows_per_tile, plan.KS, row, kglob)] = v;
+    };
     for (int a = 0; a < plan.n_acc; a++) {
         const int d = plan.dim[a], k0 = plan.kstep0[a] * 8, Ka = plan.ksteps[a] * 8;
         double nrm = 0.0;
         for (int j = 0; j < d; j++) {
             const double x = real ? X[row * D + plan.start[a] + j] : 0.0;
             nrm += x * x;
-            const float hi = to_tf32((float)x);
-            const float lo = to_tf32((float)(x - (double)hi));
-            float e0, e1, e2;
-            if (side == 0) { e0 = hi; e1 = hi; e2 = lo; }
-            else { e0 = -2.f * hi; e1 = -2.f * lo; e2 = -2.f * hi; }
-            out[tc_elem_offset(rows_per_tile, plan.KS, row, k0 + j)] = e0;
-            out[tc_elem_offset(rows_per_tile, plan.KS, row, k0 + d + j)] = e1;
-            out[tc_elem_offset(rows_per_tile, plan.KS, row, k0 + 2 * d + j)] = e2;
+            const float t = to_tf32((float)x);
+            put(k0 + j, side == 0 ? t : -2.f * t);
         }
         float nh = to_tf32((float)nrm);
-        float nl = to_tf32((float)(nrm - (double)nh));
-        if (!real) { nh = side == 1 ? TC_BIG : 0.f; nl = 0.f; }  // padded corpus rows are infinitely far away
+        if (!real) nh = side == 1 ? TC_BIG : 0.f;   // padded corpus rows are infinitely far away
         worst = fmaxf(worst, (float)nrm);
-        const float tail[4] = {side == 0 ? nh : 1.f, side == 0 ? nl : 1.f, side == 0 ? 1.f : nh, side == 0 ? 1.f : nl};
-        for (int j = 0; j < 4; j++) out[tc_elem_offset(rows_per_tile, plan.KS, row, k0 + 3 * d + j)] = tail[j];
-        for (int j = 3 * d + 4; j < Ka; j++) out[tc_elem_offset(rows_per_tile, plan.KS, row, k0 + j)] = 0.f;
+        put(k0 + d, side == 0 ? nh : 1.f);
+        put(k0 + d + 1, side == 0 ? 1.f : nh);
+        for (int j = d + 2; j < Ka; j++) put(k0 + j, 0.f);
     }
     if (real) atomicMax(max_norm_bits, __float_as_uint(worst));  // non-negative floats order like unsigned ints
 }
@@ -158,51 +164,115 @@ __global__ void __launch_bounds__(128) knn_tc_prep_kernel(const double* __restri
 // main kernel: grid (query tiles, corpus splits)
 // ---------------------------------------------------------------------------------------------
 struct TcParams {
-    const float* A;      // prepared queries  [q tiles][KS][128 x 8]
-    const float* B;      // prepared corpus   [c tiles][KS][tn x 8]
+    const float* A;      // prepared queries  [Q padded to 128][8 KS], row-major
+    const float* B;      // prepared corpus   [c tiles][KS][tn x 8], UMMA layout
     int64_t Q, N;
     int64_t tiles_per_split;  // corpus tiles per split
     int64_t n_ctiles;
-    int kc;                   // candidates kept per row and split
+    int m;                    // entries a compaction keeps (at least)
+    int kc;                   // output slots per row and list = m + TC_SLACK
     float* part_key;          // [split][half][Q][kc]
     int* part_idx;
+    float* part_tau;          // [split][half][Q]: every point NOT in the list has a coarse value >= tau
     TcPlan plan;
 };
+
+// Warp-cooperative compaction of lane `src`'s candidate list (n entries at keys/idx + base): bisect (over the ordered
+// bit patterns of the keys) for the smallest threshold T that keeps at least m entries, stop as soon as the kept count
+// is within [m, m + TC_SLACK]; entries with key < T move to the front.  Returns (kept count, T) to every lane.  If ties
+// make it impossible to get under TC_TRIG entries, reports keep = -1: the caller closes the list (the row is then
+// recomputed by the exact kernel).
+__device__ __forceinline__ void tc_compact(float* keys, int* idx, int n, int m, int lane, int* kept_out, float* thr_out) {
+    constexpr int PER = (TC_LIST + 31) / 32;
+    float k[PER];
+    uint32_t u[PER];
+    int id[PER];
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const int e = lane + 32 * j;
+        const bool have = e < n;
+        k[j] = have ? keys[e] : 0.f;
+        id[j] = have ? idx[e] : -1;
+        u[j] = have ? f2ord(k[j]) : 0xffffffffu;
+        if (have) { lo = min(lo, u[j]); hi = max(hi, u[j]); }
+    }
+    lo = __reduce_min_sync(TC_FULL, lo);
+    hi = __reduce_max_sync(TC_FULL, hi);
+    // invariant: count(u < lo) < m <= count(u < hi_x), hi_x = hi + 1 (everything)
+    uint64_t L = lo, H = (uint64_t)hi + 1;
+    uint32_t T = (uint32_t)min(H, (uint64_t)0xffffffffu);
+    int cnt = n;
+    while (H - L > 1) {
+        const uint64_t mid = L + ((H - L) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) c += (uint64_t)u[j] < mid ? 1 : 0;   // (absent entries are 0xffffffff: never below mid <= hi)
+        c = __reduce_add_sync(TC_FULL, c);
+        if (c >= m) {
+            H = mid;
+            T = (uint32_t)mid;
+            cnt = c;
+            if (c <= m + TC_SLACK) break;
+        } else {
+            L = mid;
+        }
+    }
+    if (cnt > m + TC_SLACK && cnt > TC_TRIG) {   // more ties than the list can ever shed
+        *kept_out = -1;
+        *thr_out = -3.0e38f;
+        return;
+    }
+    __syncwarp();
+    int pos = 0;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const bool keep = u[j] < T && (lane + 32 * j) < n;
+        const unsigned bal = __ballot_sync(TC_FULL, keep);
+        if (keep) {
+            const int o = pos + __popc(bal & ((1u << lane) - 1u));
+            keys[o] = k[j];
+            idx[o] = id[j];
+        }
+        pos += __popc(bal);
+        __syncwarp();   // slots written in round j were read (into registers) before the loop: no hazard, but keep rounds ordered
+    }
+    *kept_out = pos;
+    *thr_out = ord2f(T);
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const TcPlan& plan = p.plan;
-    const int KS = plan.KS, tn = plan.tn, n_acc = plan.n_acc, kc = p.kc;
-    const uint32_t a_bytes = (uint32_t)KS * TC_TM * 32;
+    const int KS = plan.KS, tn = plan.tn, n_acc = plan.n_acc, n_stages = plan.stages;
     const uint32_t b_bytes = (uint32_t)KS * tn * 32;
-    unsigned char* sA = smem_raw;
-    unsigned char* sB = sA + a_bytes;
-    float* hk = reinterpret_cast<float*>(sB + (size_t)TC_STAGES * b_bytes);   // [kc][2 * 128] heaps (two column halves per row)
-    int* hi = reinterpret_cast<int*>(hk + (size_t)kc * 2 * TC_TM);             // [kc][2 * 128]
-    float* stg_k = reinterpret_cast<float*>(hi + (size_t)kc * 2 * TC_TM);      // [TC_STG][2 * 128] staged candidates
-    int* stg_i = reinterpret_cast<int*>(stg_k + (size_t)TC_STG * 2 * TC_TM);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_i + (size_t)TC_STG * 2 * TC_TM);
+    unsigned char* sB = smem_raw;
+    constexpr int LSTR = TC_LIST + 1;   // odd stride: the 32 lanes of a warp append to 32 different banks
+    float* lk = reinterpret_cast<float*>(sB + (size_t)n_stages * b_bytes);       // [2 * 128][LSTR] candidate keys
+    int* li = reinterpret_cast<int*>(lk + (size_t)2 * TC_TM * LSTR);              // [2 * 128][LSTR] candidate indices
+    uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)2 * TC_TM * LSTR);  // (2 * 128 * LSTR ints: a multiple of 8 bytes)
     uint64_t* full_b = bars;                    // [STAGES] corpus tile landed
     uint64_t* empty_b = bars + TC_STAGES;       // [STAGES] corpus tile consumed by the MMAs
-    uint64_t* a_full = bars + 2 * TC_STAGES;    // query tile landed
+    uint64_t* a_full = bars + 2 * TC_STAGES;    // query tile written to tensor memory (4 warps arrive)
     uint64_t* tm_full = a_full + 1;             // [2] accumulators ready
     uint64_t* tm_empty = tm_full + 2;           // [2] accumulators drained by the epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
-    // issue table of the MMA thread, one entry per K step: A descriptor, B descriptor of stage 0, accumulator column
-    // offset | accumulate flag << 31.  Building descriptors inside the issue loop (address conversion, 64-bit shifts,
-    // plan look-ups) cost the single issuing thread more cycles per instruction than the tensor pipe needs to run it.
-    uint64_t* iss_a = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // [KS]
-    uint64_t* iss_b = iss_a + TC_MAX_KS;                              // [KS]
-    uint32_t* iss_d = reinterpret_cast<uint32_t*>(iss_b + TC_MAX_KS); // [KS]
+    // issue table of the MMA thread, one entry per K step: B descriptor of stage 0, A column, accumulator column
+    // offset | accumulate flag << 31 (descriptor arithmetic inside the issue loop costs the single issuing thread more
+    // cycles per instruction than the tensor pipe needs to run it)
+    uint64_t* iss_b = reinterpret_cast<uint64_t*>(tmem_slot + 2);    // [KS]
+    uint32_t* iss_a = reinterpret_cast<uint32_t*>(iss_b + TC_MAX_KS); // [KS]
+    uint32_t* iss_d = iss_a + TC_MAX_KS;                              // [KS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int buf_cols = n_acc * tn;            // TMEM columns per accumulator buffer
+    const uint32_t a_col0 = (uint32_t)(2 * buf_cols);   // the query operand sits behind the two accumulator buffers
     uint32_t alloc_cols = 32;
-    while ((int)alloc_cols < 2 * buf_cols) alloc_cols <<= 1;
+    while (alloc_cols < a_col0 + (uint32_t)(8 * KS)) alloc_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        mbar_init(a_full, 1);
+        mbar_init(a_full, 4);
         for (int b = 0; b < 2; b++) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 8); }
         mbar_fence_init();
     }
@@ -211,8 +281,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         for (int a = 0; a < n_acc; a++)
             for (int ks = lane; ks < plan.ksteps[a]; ks += 32) {
                 const int kg = plan.kstep0[a] + ks;
-                iss_a[kg] = umma_desc(sA + (size_t)kg * TC_TM * 32);
                 iss_b[kg] = umma_desc(sB + (size_t)kg * tn * 32);
+                iss_a[kg] = a_col0 + (uint32_t)(8 * kg);
                 iss_d[kg] = (uint32_t)(a * tn) | (ks > 0 ? 0x80000000u : 0u);
             }
     }
@@ -227,17 +297,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
     const int64_t n_tiles = max((int64_t)0, t1 - t0);
 
     if (warp == 0) {
-        // ===== producer: one bulk copy per operand tile =====
+        // ===== producer: one bulk copy per corpus tile =====
         if (lane == 0) {
-            mbar_arrive_expect_tx(a_full, a_bytes);
-            bulk_g2s(sA, p.A + (size_t)qtile * KS * TC_TM * 8, a_bytes, a_full);
             int s = 0;
             uint32_t ph = 0;
             for (int64_t t = 0; t < n_tiles; ++t) {
                 mbar_wait(&empty_b[s], ph ^ 1);
                 mbar_arrive_expect_tx(&full_b[s], b_bytes);
                 bulk_g2s(sB + (size_t)s * b_bytes, p.B + (size_t)(t0 + t) * KS * tn * 8, b_bytes, &full_b[s]);
-                if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+                if (++s == n_stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -245,6 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(tn);
             mbar_wait(a_full, 0);
+            tc_fence_after();
             int s = 0;
             uint32_t ph = 0;
             for (int64_t t = 0; t < n_tiles; ++t) {
@@ -258,47 +327,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
 #pragma unroll 4
                 for (int kg = 0; kg < KS; kg++) {
                     const uint32_t d = iss_d[kg];
-                    umma_tf32(d_base + (d & 0x7fffffffu), iss_a[kg], iss_b[kg] + stage_off, idesc, d >> 31);
+                    umma_tf32_ts(d_base + (d & 0x7fffffffu), tmem_base + iss_a[kg], iss_b[kg] + stage_off, idesc, d >> 31);
                 }
                 umma_commit(&empty_b[s]);     // the stage may be refilled once these MMAs have read it
                 umma_commit(&tm_full[buf]);   // accumulators complete
-                if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+                if (++s == n_stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: 8 warps; thread = (query row, half); 16-column chunks alternate between halves =====
+        // ===== epilogue: 8 warps; thread = (query row, half); 16-column chunks alternate between the halves =====
         const int quarter = warp & 3, half = (warp - 4) >> 2;
         const int r_in_tile = quarter * 32 + lane;
-        const int hslot = half * TC_TM + r_in_tile;            // this thread's heap / staging column
         const int64_t row = qtile * TC_TM + r_in_tile;
-        ThreadHeap<float> heap(hk + hslot, hi + hslot, 2 * TC_TM, kc, 0);
-        float* sk = stg_k + hslot;                             // staging [TC_STG][2 * TC_TM]
-        int* si = stg_i + hslot;
-        int staged = 0;
-        float thr = 3.0e38f;
-        const int chunks_per_tile = tn >> 4;   // 16-column chunks: the loads of up to four robots' accumulators fly together
-        // every lane pushes its staged candidates into its own heap at the same time: the sift loops of the 32
-        // lanes run side by side instead of one lane at a time
-        auto flush = [&]() {
-            for (int e = 0; e < staged; e++) {
-                const float key = sk[e * 2 * TC_TM];
-                const int idx = si[e * 2 * TC_TM];
-                if (heap.accepts(key, idx)) heap.push(key, idx);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        if (half == 0) {
+            // the query rows of this lane quarter -> tensor memory (A operand of every MMA of this CTA)
+            const float4* arow = reinterpret_cast<const float4*>(p.A + (size_t)row * (size_t)(KS * 8));
+            for (int ks = 0; ks < KS; ks++) {
+                float v[8];
+                const float4 x0 = arow[2 * ks], x1 = arow[2 * ks + 1];
+                v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+                tmem_st8(lane_addr + a_col0 + (uint32_t)(8 * ks), v);
             }
-            staged = 0;
-            if (heap.full()) thr = heap.top_key();
-        };
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+        const int hslot = half * TC_TM + r_in_tile;            // this thread's list
+        float* mk = lk + (size_t)hslot * LSTR;
+        int* mi = li + (size_t)hslot * LSTR;
+        float* wk = lk + (size_t)(hslot - lane) * LSTR;        // list of lane 0 of this warp (lists of a warp are consecutive)
+        int* wi = li + (size_t)(hslot - lane) * LSTR;
+        int n = 0;                                             // entries in the list
+        float thr = 3.0e38f;                                   // append what is below; everything dropped so far was >= tau
+        float tau = 3.0e38f;
+        const int m = p.m;
+        const int chunks_per_tile = tn >> 4;   // 16-column chunks: the loads of up to four robots' accumulators fly together
         for (int64_t t = 0; t < n_tiles; ++t) {
             const int buf = (int)(t & 1);
             const uint32_t use = (uint32_t)(t >> 1);
             mbar_wait(&tm_full[buf], use & 1);
             tc_fence_after();
             const int64_t col0 = (t0 + t) * tn;
-            // the two halves take alternate chunks (chunks_per_tile is even, so the parity of a chunk is that of ci)
-            for (int ci = half; ci < chunks_per_tile; ci += 2) {
+            // the two halves take alternate chunks; the parity flips from tile to tile so that an odd number of chunks
+            // per tile is shared evenly
+            for (int ci = (half + (int)(t & 1)) & 1; ci < chunks_per_tile; ci += 2) {
                 const int c = ci << 4;
                 float v[16], b1[16], b2[16], b3[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * buf_cols + c);
+                const uint32_t taddr = lane_addr + (uint32_t)(buf * buf_cols + c);
                 // issue every accumulator's load before the one wait (n_acc is uniform across the CTA)
                 tmem_ld16(taddr, v);
                 if (n_acc > 1) tmem_ld16(taddr + (uint32_t)tn, b1);
@@ -328,51 +405,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
                     }
                 }
                 // after warm-up hardly any chunk holds a candidate: one min tree + one compare per lane, and the
-                // per-column mask only when some lane of the warp needs it
+                // per-column work only when some lane of the warp needs it
                 float lo8[8], lo4[4];
 #pragma unroll
                 for (int j = 0; j < 8; j++) lo8[j] = fminf(v[j], v[8 + j]);
 #pragma unroll
                 for (int j = 0; j < 4; j++) lo4[j] = fminf(lo8[j], lo8[4 + j]);
                 const float lo = fminf(fminf(lo4[0], lo4[1]), fminf(lo4[2], lo4[3]));
-                if (!__any_sync(0xffffffffu, lo < thr)) continue;
-                uint32_t mask = 0u;
+                if (!__any_sync(TC_FULL, lo < thr)) continue;
+                if (lo < thr) {
+                    const int64_t cbase = col0 + c;
+                    const int lim = (int)min((int64_t)16, p.N - cbase);   // columns of this chunk that exist (last tile)
+                    // append-only: no ordering, no search (n <= TC_TRIG here: room for all 16).  lo4[g] is the minimum
+                    // of columns g, g + 4, g + 8, g + 12: only groups that hold a candidate look at their members
 #pragma unroll
-                for (int j = 0; j < 16; j++) mask |= (v[j] < thr ? 1u : 0u) << j;
-                while (mask) {  // a handful of candidates per chunk and warp
-                    const int j = __ffs(mask) - 1;
-                    mask &= mask - 1u;
-                    // v[j] with a run-time j: four levels of selects keep v in registers
-                    float s8[8], s4[4], s2[2];
+                    for (int g = 0; g < 4; g++) {
+                        if (lo4[g] < thr) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) s8[i] = (j & 8) ? v[8 + i] : v[i];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) s4[i] = (j & 4) ? s8[4 + i] : s8[i];
-#pragma unroll
-                    for (int i = 0; i < 2; i++) s2[i] = (j & 2) ? s4[2 + i] : s4[i];
-                    const float val = (j & 1) ? s2[1] : s2[0];
-                    const int64_t col = col0 + c + j;
-                    if (col < p.N) {
-                        if (staged == TC_STG) flush();  // only while the heap is still filling up
-                        sk[staged * 2 * TC_TM] = val;
-                        si[staged * 2 * TC_TM] = (int)col;
-                        staged++;
+                            for (int jj = 0; jj < 4; jj++) {
+                                const int j = g + 4 * jj;
+                                if (v[j] < thr && j < lim) {
+                                    mk[n] = v[j];
+                                    mi[n] = (int)cbase + j;
+                                    n++;
+                                }
+                            }
+                        }
                     }
                 }
-                if (__any_sync(0xffffffffu, staged >= TC_STG - 2)) flush();
+                // lists that could not take another chunk are compacted, one list at a time, by the whole warp
+                unsigned need = __ballot_sync(TC_FULL, n > TC_TRIG);
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1u;
+                    const int cnt = __shfl_sync(TC_FULL, n, src);
+                    __syncwarp();
+                    int kept;
+                    float nt;
+                    tc_compact(wk + (size_t)src * LSTR, wi + (size_t)src * LSTR, cnt, m, lane, &kept, &nt);
+                    if (lane == src) {
+                        if (kept < 0) { n = 0; thr = -3.0e38f; tau = -3.0e38f; }   // closed: exact fallback for this row
+                        else { n = kept; thr = nt; tau = nt; }
+                    }
+                    __syncwarp();
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tm_empty[buf]);
         }
-        flush();
-        if (row < p.Q) {
-            float* ok = p.part_key + (((size_t)blockIdx.y * 2 + half) * p.Q + row) * kc;
-            int* oi = p.part_idx + (((size_t)blockIdx.y * 2 + half) * p.Q + row) * kc;
-            for (int e = 0; e < kc; e++) {
-                ok[e] = e < heap.n ? heap.key[e * 2 * TC_TM] : 3.0e38f;
-                oi[e] = e < heap.n ? heap.idx[e * 2 * TC_TM] : -1;
+        // final compaction to the output size (every list longer than kc), then write-out
+        {
+            unsigned need = __ballot_sync(TC_FULL, n > p.kc);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1u;
+                const int cnt = __shfl_sync(TC_FULL, n, src);
+                __syncwarp();
+                int kept;
+                float nt;
+                tc_compact(wk + (size_t)src * LSTR, wi + (size_t)src * LSTR, cnt, m, lane, &kept, &nt);
+                if (lane == src) {
+                    if (kept < 0 || kept > p.kc) { n = 0; tau = -3.0e38f; }
+                    else { n = kept; tau = nt; }
+                }
+                __syncwarp();
             }
+        }
+        if (row < p.Q) {
+            const size_t lst = ((size_t)blockIdx.y * 2 + half) * p.Q + row;
+            float* ok = p.part_key + lst * p.kc;
+            int* oi = p.part_idx + lst * p.kc;
+            for (int e = 0; e < p.kc; e++) {
+                ok[e] = e < n ? mk[e] : 3.0e38f;
+                oi[e] = e < n ? mi[e] : -1;
+            }
+            p.part_tau[lst] = tau;
         }
     }
     tc_fence_before();
@@ -387,7 +495,8 @@ template <int DMAX>
 __global__ void __launch_bounds__(128) knn_rerank_kernel(const double* __restrict__ queries, const double* __restrict__ corpus, int64_t Q,
                                                          int D, const __grid_constant__ Slices sl, int metric, int k, int kc,
                                                          int splits, const float* __restrict__ part_key, const int* __restrict__ part_idx,
-                                                         const unsigned* __restrict__ max_norm_bits, int32_t* __restrict__ out_idx,
+                                                         const float* __restrict__ part_tau,
+                                                         unsigned* __restrict__ max_norm_bits, int32_t* __restrict__ out_idx,
                                                          double* __restrict__ out_dist, uint8_t* __restrict__ certified) {
     extern __shared__ __align__(16) unsigned char smem_rr[];
     double* hk = reinterpret_cast<double*>(smem_rr);
@@ -400,21 +509,18 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const double* __restric
     ThreadHeap<double> heap(hk + threadIdx.x, hi + threadIdx.x, 128, k, 0);
     float tau = 3.0e38f;  // smallest coarse value any discarded point can have
     for (int s = 0; s < splits; s++) {
-        const float* pk = part_key + ((size_t)s * Q + row) * kc;
         const int* pi = part_idx + ((size_t)s * Q + row) * kc;
-        float worst = -3.0e38f;
-        bool full = true;
         for (int e = 0; e < kc; e++) {
             const int idx = pi[e];
-            if (idx < 0) { full = false; continue; }
-            worst = fmaxf(worst, pk[e]);
+            if (idx < 0) continue;
             const double d = metric_dist<DMAX>(q, corpus + (size_t)idx * D, D, sl, metric);
             if (heap.accepts(d, idx)) heap.push(d, idx);
         }
-        if (full) tau = fminf(tau, worst);  // a split whose list is not full kept all of its points
+        tau = fminf(tau, part_tau[(size_t)s * Q + row]);   // every point outside list s has a coarse value >= its tau
     }
-    // coarse values carry an absolute error of a few 2^-22 of the largest squared norms involved
-    const float eps = 8e-6f * (2.f * __uint_as_float(*max_norm_bits) + 1.f);
+    // error bound of a coarse value (single TF32 rounding of every operand entry, exact products, FP32 accumulation):
+    // (2^-9 + 2^-10) * M for the cross and norm terms, M = largest squared slice norm of any query / corpus row
+    const float eps = 2.95e-3f * __uint_as_float(max_norm_bits[0]) + 1e-4f;
     bool ok = true;
     if (heap.n == k) {
         const double dk = heap.top_key();
@@ -423,6 +529,7 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const double* __restric
         ok = tau > 1.0e38f;  // fewer than k found: fine only if nothing was discarded anywhere
     }
     certified[row] = ok ? 1 : 0;
+    if (!ok) atomicAdd(&max_norm_bits[1], 1u);   // statistics: rows handed to the exact kernel
     const int found = heap.n;
     for (int e = found - 1; e >= 0; e--) {
         double d;
@@ -458,16 +565,40 @@ bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan) {
     }
     for (int a = 0; a < plan->n_acc; a++) {
         plan->kstep0[a] = plan->KS;
-        plan->ksteps[a] = pad8(3 * plan->dim[a] + 4) / 8;
+        plan->ksteps[a] = pad8(plan->dim[a] + 2) / 8;
         plan->KS += plan->ksteps[a];
     }
-    int tn = 256 / plan->n_acc;
-    plan->tn = tn >= 256 ? 256 : tn >= 128 ? 128 : tn >= 64 ? 64 : 32;
-    return plan->KS <= TC_MAX_KS;
+    if (plan->KS > TC_MAX_KS) return false;
+    // tensor memory: two accumulator buffers of n_acc x tn columns and the query operand (8 columns per K step) in 512
+    // columns; the UMMA N of a 128-row instruction is a multiple of 16
+    int tn = (512 - 8 * plan->KS) / (2 * plan->n_acc) / 16 * 16;
+    if (tn > 256) tn = 256;
+    // shared memory: the candidate lists take 2 * 128 * (TC_LIST + 1) * 8 bytes; the corpus stages share the rest
+    const long avail = 224L * 1024 - (long)2 * TC_TM * (TC_LIST + 1) * 8 - 4096;
+    int stages = 0;
+    for (; tn >= 16; tn -= 16) {
+        stages = (int)(avail / ((long)plan->KS * tn * 32));
+        if (stages >= 2) break;
+    }
+    if (tn < 16) return false;
+    plan->tn = tn;
+    plan->stages = stages > TC_STAGES ? TC_STAGES : stages;
+    return true;
 }
 
-size_t knn_tc_smem_bytes(const TcPlan& plan, int kc) {
-    return (size_t)plan.KS * TC_TM * 32 + (size_t)TC_STAGES * plan.KS * plan.tn * 32 + (size_t)(kc + TC_STG) * 2 * TC_TM * 8 + 16 * 8 + (size_t)TC_MAX_KS * 20 + 1024;
+// entries a compaction keeps per list: the k nearest spread over n_lists lists binomially -- mean + 4 sigma + 2
+int knn_tc_keep(int k, int n_lists) {
+    const double pr = 1.0 / n_lists;
+    int m = (int)(k * pr + 4.0 * sqrt(k * pr * (1.0 - pr)) + 2.999);
+    if (m > k + 8) m = k + 8;
+    if (m > TC_TRIG - 16) m = TC_TRIG - 16;
+    return m < 1 ? 1 : m;
+}
+int knn_tc_slots(int k, int n_lists) { return knn_tc_keep(k, n_lists) + TC_SLACK; }
+int knn_tc_max_k() { return TC_TRIG - 16 - 8; }
+
+size_t knn_tc_smem_bytes(const TcPlan& plan, int /*kc*/) {
+    return (size_t)plan.stages * plan.KS * plan.tn * 32 + (size_t)2 * TC_TM * (TC_LIST + 1) * 8 + 16 + 16 * 8 + (size_t)TC_MAX_KS * 16 + 1024;
 }
 
 int knn_tc_splits(int64_t Q, int64_t n_ctiles) {
@@ -485,7 +616,7 @@ int knn_tc_splits(int64_t Q, int64_t n_ctiles) {
 
 size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, int splits) {
     const int64_t qt = (Q + TC_TM - 1) / TC_TM, ct = (N + plan.tn - 1) / plan.tn;
-    return (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)splits * 2 * Q * kc * 8 + (size_t)Q + 1024;
+    return 256 + (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)splits * 2 * Q * (kc * 8 + 4) + 1024;
 }
 
 cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
@@ -502,7 +633,9 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     float* part_key = (float*)w;
     w += (size_t)splits * 2 * Q * kc * 4;
     int* part_idx = (int*)w;
-    cudaError_t e = cudaMemsetAsync(max_norm, 0, 4, st);
+    w += (size_t)splits * 2 * Q * kc * 4;
+    float* part_tau = (float*)w;
+    cudaError_t e = cudaMemsetAsync(max_norm, 0, 8, st);   // [0] largest squared slice norm, [1] rows handed to the exact kernel
     if (e != cudaSuccess) return e;
     knn_tc_prep_kernel<<<(unsigned)((qt * TC_TM + 127) / 128), 128, 0, st>>>(queries, Q, qt * TC_TM, D, plan, 0, TC_TM, A, max_norm);
     knn_tc_prep_kernel<<<(unsigned)((ct * plan.tn + 127) / 128), 128, 0, st>>>(corpus, N, ct * plan.tn, D, plan, 1, plan.tn, B, max_norm);
@@ -513,9 +646,11 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     p.N = N;
     p.n_ctiles = ct;
     p.tiles_per_split = (ct + splits - 1) / splits;
+    p.m = kc - TC_SLACK;
     p.kc = kc;
     p.part_key = part_key;
     p.part_idx = part_idx;
+    p.part_tau = part_tau;
     p.plan = plan;
     const size_t smem = knn_tc_smem_bytes(plan, kc);
     e = cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -529,7 +664,7 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
         e = cudaFuncSetAttribute(knn_rerank_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);                 \
         if (e != cudaSuccess) return e;                                                                                           \
         knn_rerank_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, rsmem, st>>>(queries, corpus, Q, D, sl, metric, k, kc, 2 * splits,  \
-                                                                               part_key, part_idx, max_norm, out_idx, out_dist,  \
+                                                                               part_key, part_idx, part_tau, max_norm, out_idx, out_dist,  \
                                                                                certified);                                        \
     } while (0)
     if (D <= 8) MRB_RERANK(8);

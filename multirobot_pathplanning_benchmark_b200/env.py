@@ -497,8 +497,15 @@ if HAVE_REFERENCE:
                 cand.slot, cand.ticket = self._slot, None
                 self.spec_cache.stats["candidate_reissues"] += 1
             elif cand.first is None:
-                _, first = dev.collect_edges(cand.ticket, len(cand.N))
-                cand.first = np.asarray(first, np.int32)
+                try:
+                    _, first = dev.collect_edges(cand.ticket, len(cand.N))
+                except Exception:      # the ticket has expired (many newer batches since): run the batch again, synchronously
+                    q1 = np.frombuffer(q1_bytes, np.float64)
+                    _, first = dev.check_edges(self._slot, np.repeat(q1[None].astype(np.float32), len(cand.N), 0),
+                                               cand.q2.astype(np.float32), params[0], N=cand.N)
+                    first = CudaDevice.to_numpy(first)
+                    self.spec_cache.stats["candidate_reissues"] += 1
+                cand.first = np.array(first, np.int32)
             self.spec_cache.stats["candidate_hits"] += 1
             return int(cand.first[i])
 

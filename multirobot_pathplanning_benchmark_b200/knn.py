@@ -86,8 +86,11 @@ def prm_r_star(N: int, D: int, informed_measure: float = 1.0) -> float:
     return 1.001 * 2 * (informed_measure / unit_ball * (math.log(N) / N) * (1 + 1 / D)) ** (1 / D)
 
 
+LAST_STATS = {}   # filled by batch_knn(..., stats=True): {"uncertified_rows": rows the tensor path handed to the exact kernel}
+
+
 def batch_knn(queries: torch.Tensor, corpus: torch.Tensor, slices=None, metric: str = "max_euclidean", k: int = 1,
-              mode: str = "auto", return_dist: bool = True):
+              mode: str = "auto", return_dist: bool = True, stats: bool = False):
     """k nearest corpus rows of every query row, ascending (distance, index).
     -> (idx [Q, k] int32, dist [Q, k] float64); missing neighbours are -1 / inf."""
     lib = _lib.load()
@@ -107,6 +110,11 @@ def batch_knn(queries: torch.Tensor, corpus: torch.Tensor, slices=None, metric: 
                                   s.ctypes.data_as(_lib.c_i32p) if s is not None else None, R, METRICS[metric], int(k),
                                   idx.data_ptr(), dist.data_ptr() if dist is not None else None, ws.data_ptr(), ws_bytes,
                                   {"auto": 0, "exact": 1, "tensor": 2}[mode], _stream(dev)), "knn")
+        if stats:   # (synchronises)
+            off = int(lib.mrb200_knn_stats_offset(Q, N, D, k))
+            st = ws[off:off + 8].view(torch.int32).cpu().numpy()
+            LAST_STATS.clear()
+            LAST_STATS.update({"uncertified_rows": int(st[1]), "max_sq_slice_norm": float(np.int32(st[0]).view(np.float32))})
     return (idx, dist) if return_dist else idx
 
 

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
 KEEP = ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "launch__", "sm__inst_executed_pipe_", "sm__pipe_tensor",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__average_warp", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__average_warp", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct", "smsp__cycles_elapsed.avg", "sm__issue_active.avg", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__sass_thread_inst_executed_op_f", "dram__throughput.avg.pct",
         "lts__t_sector_hit_rate.pct", "sm__cycles_active.avg", "smsp__cycles_active.avg", "smsp__warp_issue_stalled", "sm__cycles_elapsed.max")
 WORKLOAD_OF = {"configs_box_rearrangement_4M": ("box_rearrangement_4M", 4194304), "configs_box_stacking_1M": ("box_stacking_1M", 1048576),
@@ -47,13 +47,18 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"cap_{TAG}_*.ncu-r
         if scale_unit:
             val *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1, "us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}.get(unit, 1)
         return val
-    ffma, fadd, fmul = (g(f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum", False) or 0 for o in ("ffma", "fadd", "fmul"))
+    # thread instructions per elapsed cycle (summed over the SM sub-partitions) x elapsed cycles
+    cyc = g("smsp__cycles_elapsed.avg", False) or 0
+    ffma, fadd, fmul = ((g(f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum.per_cycle_elapsed", False) or 0) * cyc
+                        for o in ("ffma", "fadd", "fmul"))
     stall_noinst = g("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", False)
     if stall_noinst is None:
         stall_noinst = g("smsp__average_warp_latency_issue_stalled_no_instruction.ratio", False)
     entry = {"source": f"{txt} (ncu --set full of the round-{TAG} build)", "kernel": v[hdr.index("Kernel Name")][:60],
              "kernel_ms": g("gpu__time_duration.sum"), "dram_bytes": (g("dram__bytes_read.sum") or 0) + (g("dram__bytes_write.sum") or 0),
-             "executed_fp32_flop": 2 * ffma + fadd + fmul, "issue_active_pct": g("smsp__issue_active.avg.pct", False),
+             "executed_fp32_flop": 2 * ffma + fadd + fmul, "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active", False),
+             "sm_throughput_pct": g("sm__throughput.avg.pct_of_peak_sustained_elapsed", False),
+             "warp_instructions": g("smsp__inst_executed.sum", False),
              "warps_active_pct": g("sm__warps_active.avg.pct_of_peak_sustained_active", False),
              "registers": g("launch__registers_per_thread", False), "no_instruction_stall": stall_noinst,
              "tensor_pipe_active_pct": g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", False)}

@@ -24,7 +24,7 @@ if what in ("configs", "edges"):
             be.set_two_phase(0, sys.argv[4])
         for _ in range(5):
             f = be.check_configs(0, q)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()   # (lets the slot's two-phase policy settle before the captured launch)
         print(name, n, "free", f.float().mean().item())
     else:
         kind = sys.argv[4] if len(sys.argv) > 4 else "local"

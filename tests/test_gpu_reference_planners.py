@@ -73,9 +73,11 @@ def test_speculative_cache_on_the_real_device(envmod):
     spec = envmod.b200_two_dim_handover(speculate=True)
     plain = envmod.b200_two_dim_handover(speculate=False)
     np.random.seed(11)
-    qs = [spec.sample_config_uniform_in_limits() for _ in range(1500)]   # spans two sample blocks
-    got = [spec.is_collision_free(q, spec.start_mode) for q in qs]
-    want = [plain.is_collision_free(q, plain.start_mode) for q in qs]
+    got, want = [], []
+    for _ in range(1500):   # spans two sample blocks; the planners query each sample right after drawing it
+        q = spec.sample_config_uniform_in_limits()
+        got.append(spec.is_collision_free(q, spec.start_mode))
+        want.append(plain.is_collision_free(q, plain.start_mode))
     assert got == want and 0 < sum(got) < len(got)
     assert spec.spec_cache.stats["config_launches"] == 2 and spec.spec_cache.stats["config_hits"] == 1498
     rng = np.random.RandomState(4)
