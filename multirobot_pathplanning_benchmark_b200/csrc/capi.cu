@@ -721,7 +721,7 @@ static size_t tc_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
     const int splits = tc_max_splits(Q);
     const size_t lists = (size_t)splits * 2;
     return 256 + align256((size_t)((Q + 127) / 128) * ks * 128 * 32) + align256((size_t)(N + 256) * ks * 32) +
-           align256(lists * (size_t)Q * ((size_t)(k + 16) * 8 + 4)) + align256((size_t)Q) + 4096;
+           align256(lists * (size_t)Q * ((size_t)(k + 16) * 8 + 4)) + align256((size_t)Q * 4 + 16) + align256((size_t)1024 * 32 * (size_t)k * 12) + align256((size_t)Q) + 4096;
 }
 
 size_t mrb200_knn_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
@@ -764,11 +764,11 @@ int mrb200_knn(const double* queries, const double* corpus, int64_t Q, int64_t N
         cudaError_t e = mrb::launch_knn_tc(queries, corpus, Q, N, D, sl, metric, k, kc, plan, tsplits, tc_ws + align256((size_t)Q), out_idx,
                                            out_dist, certified, st);
         if (e != cudaSuccess) return cuda_fail(e, "knn (tensor-core path)");
-        g_launches += 4;
-        skip = certified;  // rows the re-rank could not certify are recomputed exactly below
+        g_launches += 6;   // 2 x operand preparation, candidate generator, re-rank, exact rows without a certificate + their merge
+        (void)skip;
+        return MRB200_OK;
     }
-    cudaError_t e = mrb::launch_knn_exact(queries, corpus, Q, N, D, sl, metric, k, use_tc ? 1 : splits, part_d, part_i, out_idx, out_dist,
-                                          skip, st);
+    cudaError_t e = mrb::launch_knn_exact(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, out_idx, out_dist, nullptr, st);
     if (e != cudaSuccess) return cuda_fail(e, "knn");
     g_launches += 2;
     return MRB200_OK;

@@ -22,7 +22,13 @@
 // for the value that keeps about `m` entries, drops the rest and lowers the threshold.  knn_rerank_kernel recomputes the
 // candidates' distances in fp64 with the reference's operand order, sorts by (distance, index) and certifies each
 // row: if the exact k-th squared distance is not below (smallest discard threshold - error bound) the row is flagged
-// and the caller recomputes it with the exact kernel (knn_kernels.cu).
+// and recomputed exactly by knn_rows_kernel.
+//
+// Measured and rejected (round 2, profiles/r2_knn_notes.md): one more accumulator holding the SUM over the robots as a
+// prefilter of the max (max_r d_r^2 >= S / R, so S >= R * threshold discards a point from one accumulator load instead
+// of R).  The per-list thresholds only approach their final value late in the corpus sweep, so about two thirds of the
+// 16-column chunks still pass the prefilter for some lane of the warp, and the extra load + MMAs made the kernel slower
+// (12.1 -> 14.5 ms at 100k x 100k, four arms).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         mbar_init(a_full, 4);
-        for (int b = 0; b < 2; b++) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 8); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 4); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, alloc_cols);
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: 8 warps; thread = (query row, half); 16-column chunks alternate between the halves =====
+        // ===== epilogue: 8 warps; thread = (query row, half); the halves alternate corpus tiles =====
         const int quarter = warp & 3, half = (warp - 4) >> 2;
         const int r_in_tile = quarter * 32 + lane;
         const int64_t row = qtile * TC_TM + r_in_tile;
@@ -364,15 +370,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         float tau = 3.0e38f;
         const int m = p.m;
         const int chunks_per_tile = tn >> 4;   // 16-column chunks: the loads of up to four robots' accumulators fly together
-        for (int64_t t = 0; t < n_tiles; ++t) {
-            const int buf = (int)(t & 1);
+        // the two halves alternate TILES: half h drains accumulator buffer h (tiles t = h, h + 2, ...), so a warp meets the
+        // barriers once per tile of its own and works through all of the tile's 16-column chunks in between
+        for (int64_t t = half; t < n_tiles; t += 2) {
+            const int buf = half;
             const uint32_t use = (uint32_t)(t >> 1);
             mbar_wait(&tm_full[buf], use & 1);
             tc_fence_after();
             const int64_t col0 = (t0 + t) * tn;
-            // the two halves take alternate chunks; the parity flips from tile to tile so that an odd number of chunks
-            // per tile is shared evenly
-            for (int ci = (half + (int)(t & 1)) & 1; ci < chunks_per_tile; ci += 2) {
+            for (int ci = 0; ci < chunks_per_tile; ++ci) {
                 const int c = ci << 4;
                 float v[16], b1[16], b2[16], b3[16];
                 const uint32_t taddr = lane_addr + (uint32_t)(buf * buf_cols + c);
@@ -496,7 +502,8 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const double* __restric
                                                          int D, const __grid_constant__ Slices sl, int metric, int k, int kc,
                                                          int splits, const float* __restrict__ part_key, const int* __restrict__ part_idx,
                                                          const float* __restrict__ part_tau,
-                                                         unsigned* __restrict__ max_norm_bits, int32_t* __restrict__ out_idx,
+                                                         unsigned* __restrict__ max_norm_bits, int* __restrict__ redo_rows,
+                                                         int32_t* __restrict__ out_idx,
                                                          double* __restrict__ out_dist, uint8_t* __restrict__ certified) {
     extern __shared__ __align__(16) unsigned char smem_rr[];
     double* hk = reinterpret_cast<double*>(smem_rr);
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const double* __restric
         ok = tau > 1.0e38f;  // fewer than k found: fine only if nothing was discarded anywhere
     }
     certified[row] = ok ? 1 : 0;
-    if (!ok) atomicAdd(&max_norm_bits[1], 1u);   // statistics: rows handed to the exact kernel
+    if (!ok) redo_rows[atomicAdd(&max_norm_bits[1], 1u)] = (int)row;   // rows handed to the exact per-row kernel below
     const int found = heap.n;
     for (int e = found - 1; e >= 0; e--) {
         double d;
@@ -541,6 +548,125 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const double* __restric
     for (int e = found; e < k; e++) {
         out_idx[row * k + e] = -1;
         if (out_dist) out_dist[row * k + e] = __longlong_as_double(0x7ff0000000000000LL);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact k-NN of the few rows the re-rank could not certify: one CTA per row, all 256 threads share the corpus
+// (thread-local bounded heaps of the k best, then a k-round block-wide merge by (distance, index)).  The streaming
+// exact kernel (knn_kernels.cu) maps one THREAD to a row: a single uncertified row would crawl through the whole
+// corpus on one thread (150 ms at N = 100 000) while its CTA neighbours idle.
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_REDO_PARTS = 32;     // CTAs sharing one uncertified row
+constexpr int TC_REDO_FAST = 1024;    // rows that get the multi-CTA treatment; any further rows take one CTA each
+
+// parts > 1: CTA (x, y) handles rows x, x + gridDim.x, ... < min(total, TC_REDO_FAST) and the y-th part of the corpus; its k
+// best go to part_d / part_i [row slot][part][k] for knn_rows_merge_kernel.  parts == 1: rows TC_REDO_FAST + x, ... and the
+// whole corpus, written straight to the output.
+template <int DMAX>
+__global__ void __launch_bounds__(256) knn_rows_kernel(const double* __restrict__ queries, const double* __restrict__ corpus, int64_t N,
+                                                       int D, const __grid_constant__ Slices sl, int metric, int k,
+                                                       const int* __restrict__ rows, const unsigned* __restrict__ n_rows,
+                                                       int parts, double* __restrict__ part_d, int* __restrict__ part_i,
+                                                       int32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                                       uint8_t* __restrict__ certified) {
+    extern __shared__ __align__(16) unsigned char smem_kr[];
+    double* hk = reinterpret_cast<double*>(smem_kr);                 // [k][256]
+    int* hi = reinterpret_cast<int*>(hk + (size_t)k * 256);          // [k][256]
+    double* red_d = reinterpret_cast<double*>(hi + (size_t)k * 256); // [8]
+    int* red_i = reinterpret_cast<int*>(red_d + 8);                  // [8] index, [8] owner thread
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned total = parts > 1 ? min(*n_rows, (unsigned)TC_REDO_FAST) : *n_rows;
+    const int64_t plen = (N + parts - 1) / parts;
+    const int64_t p0 = (int64_t)blockIdx.y * plen, p1 = min(N, p0 + plen);
+    for (unsigned r = (parts > 1 ? 0u : (unsigned)TC_REDO_FAST) + blockIdx.x; r < total; r += gridDim.x) {
+        const int64_t row = rows[r];
+        double q[DMAX];
+#pragma unroll
+        for (int d = 0; d < DMAX; d++) q[d] = d < D ? queries[row * D + d] : 0.0;
+        ThreadHeap<double> heap(hk + tid, hi + tid, 256, k, 0);
+        for (int64_t i = p0 + tid; i < p1; i += 256) {
+            const double d = metric_dist<DMAX>(q, corpus + (size_t)i * D, D, sl, metric);
+            if (heap.accepts(d, (int)i)) heap.push(d, (int)i);
+        }
+        // ascending order in place: pop the maximum into the last free slot
+        const int mine = heap.n;
+        for (int e = mine - 1; e >= 0; e--) {
+            double d;
+            int i;
+            heap.pop(&d, &i);
+            hk[(size_t)e * 256 + tid] = d;
+            hi[(size_t)e * 256 + tid] = i;
+        }
+        int head = 0;
+        __syncthreads();
+        for (int e = 0; e < k; e++) {
+            double bd = head < mine ? hk[(size_t)head * 256 + tid] : __longlong_as_double(0x7ff0000000000000LL);
+            int bi = head < mine ? hi[(size_t)head * 256 + tid] : 0x7fffffff;
+            int bt = tid;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o), ot = __shfl_xor_sync(0xffffffffu, bt, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bt = ot; }
+            }
+            if (lane == 0) { red_d[warp] = bd; red_i[warp] = bi; red_i[8 + warp] = bt; }
+            __syncthreads();
+            bd = red_d[0]; bi = red_i[0]; bt = red_i[8];
+#pragma unroll
+            for (int w = 1; w < 8; w++) {
+                const double od = red_d[w];
+                const int oi = red_i[w];
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bt = red_i[8 + w]; }
+            }
+            if (tid == 0) {
+                const bool found = bi != 0x7fffffff;
+                if (parts > 1) {
+                    const size_t o = ((size_t)r * parts + blockIdx.y) * k + e;
+                    part_d[o] = found ? bd : __longlong_as_double(0x7ff0000000000000LL);
+                    part_i[o] = found ? bi : 0x7fffffff;
+                } else {
+                    out_idx[row * k + e] = found ? bi : -1;
+                    if (out_dist) out_dist[row * k + e] = found ? bd : __longlong_as_double(0x7ff0000000000000LL);
+                }
+            }
+            if (tid == bt) head++;
+            __syncthreads();
+        }
+        if (tid == 0 && parts == 1) certified[row] = 1;
+    }
+}
+
+// k-way merge of the TC_REDO_PARTS sorted partial lists of a row: one warp per row, lane = part
+__global__ void __launch_bounds__(32) knn_rows_merge_kernel(const int* __restrict__ rows, const unsigned* __restrict__ n_rows, int k,
+                                                            const double* __restrict__ part_d, const int* __restrict__ part_i,
+                                                            int32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                                            uint8_t* __restrict__ certified) {
+    const unsigned total = min(*n_rows, (unsigned)TC_REDO_FAST);
+    const int lane = threadIdx.x;
+    for (unsigned r = blockIdx.x; r < total; r += gridDim.x) {
+        const int64_t row = rows[r];
+        const double* pd = part_d + ((size_t)r * TC_REDO_PARTS + lane) * k;
+        const int* pi = part_i + ((size_t)r * TC_REDO_PARTS + lane) * k;
+        int head = 0;
+        for (int e = 0; e < k; e++) {
+            double bd = head < k ? pd[head] : __longlong_as_double(0x7ff0000000000000LL);
+            int bi = head < k ? pi[head] : 0x7fffffff;
+            int bl = lane;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o), ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bl = ol; }
+            }
+            if (lane == 0) {
+                const bool found = bi != 0x7fffffff;
+                out_idx[row * k + e] = found ? bi : -1;
+                if (out_dist) out_dist[row * k + e] = found ? bd : __longlong_as_double(0x7ff0000000000000LL);
+            }
+            if (lane == bl) head++;
+        }
+        if (lane == 0) certified[row] = 1;
     }
 }
 
@@ -616,7 +742,7 @@ int knn_tc_splits(int64_t Q, int64_t n_ctiles) {
 
 size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, int splits) {
     const int64_t qt = (Q + TC_TM - 1) / TC_TM, ct = (N + plan.tn - 1) / plan.tn;
-    return 256 + (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)splits * 2 * Q * (kc * 8 + 4) + 1024;
+    return 256 + (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)splits * 2 * Q * (kc * 8 + 4) + (size_t)Q * 4 + 16 + (size_t)TC_REDO_FAST * TC_REDO_PARTS * (kc + 8) * 12 + 1024;
 }
 
 cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
@@ -635,6 +761,12 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     int* part_idx = (int*)w;
     w += (size_t)splits * 2 * Q * kc * 4;
     float* part_tau = (float*)w;
+    w += (size_t)splits * 2 * Q * 4;
+    int* redo_rows = (int*)w;
+    w += ((size_t)Q * 4 + 15) / 16 * 16;
+    double* redo_d = (double*)w;
+    w += (size_t)TC_REDO_FAST * TC_REDO_PARTS * k * 8;
+    int* redo_i = (int*)w;
     cudaError_t e = cudaMemsetAsync(max_norm, 0, 8, st);   // [0] largest squared slice norm, [1] rows handed to the exact kernel
     if (e != cudaSuccess) return e;
     knn_tc_prep_kernel<<<(unsigned)((qt * TC_TM + 127) / 128), 128, 0, st>>>(queries, Q, qt * TC_TM, D, plan, 0, TC_TM, A, max_norm);
@@ -664,15 +796,30 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
         e = cudaFuncSetAttribute(knn_rerank_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);                 \
         if (e != cudaSuccess) return e;                                                                                           \
         knn_rerank_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, rsmem, st>>>(queries, corpus, Q, D, sl, metric, k, kc, 2 * splits,  \
-                                                                               part_key, part_idx, part_tau, max_norm, out_idx, out_dist,  \
+                                                                               part_key, part_idx, part_tau, max_norm, redo_rows, out_idx, out_dist,  \
                                                                                certified);                                        \
     } while (0)
-    if (D <= 8) MRB_RERANK(8);
-    else if (D <= 16) MRB_RERANK(16);
-    else if (D <= 24) MRB_RERANK(24);
-    else if (D <= 32) MRB_RERANK(32);
-    else MRB_RERANK(64);
+    // rows without a certificate: exact answer from the per-row kernel (a fixed small grid; CTAs beyond the list exit)
+    const size_t ksmem = (size_t)k * 256 * 12 + 8 * 8 + 16 * 4;
+#define MRB_ROWS(DM)                                                                                                              \
+    do {                                                                                                                          \
+        e = cudaFuncSetAttribute(knn_rows_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksmem);                   \
+        if (e != cudaSuccess) return e;                                                                                           \
+        knn_rows_kernel<DM><<<dim3(64, TC_REDO_PARTS), 256, ksmem, st>>>(queries, corpus, N, D, sl, metric, k, redo_rows,        \
+                                                                         max_norm + 1, TC_REDO_PARTS, redo_d, redo_i, out_idx,    \
+                                                                         out_dist, certified);                                    \
+        knn_rows_merge_kernel<<<64, 32, 0, st>>>(redo_rows, max_norm + 1, k, redo_d, redo_i, out_idx, out_dist, certified);       \
+        if (Q > TC_REDO_FAST)                                                                                                     \
+            knn_rows_kernel<DM><<<dim3(296, 1), 256, ksmem, st>>>(queries, corpus, N, D, sl, metric, k, redo_rows, max_norm + 1,  \
+                                                                  1, nullptr, nullptr, out_idx, out_dist, certified);             \
+    } while (0)
+    if (D <= 8) { MRB_RERANK(8); MRB_ROWS(8); }
+    else if (D <= 16) { MRB_RERANK(16); MRB_ROWS(16); }
+    else if (D <= 24) { MRB_RERANK(24); MRB_ROWS(24); }
+    else if (D <= 32) { MRB_RERANK(32); MRB_ROWS(32); }
+    else { MRB_RERANK(64); MRB_ROWS(64); }
 #undef MRB_RERANK
+#undef MRB_ROWS
     return cudaGetLastError();
 }
 
