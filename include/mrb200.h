@@ -168,6 +168,19 @@ int mrb200_knn(const double* queries_dev /*[Q, D]*/, const double* corpus_dev /*
                int D, const int32_t* slices_host, int R, int metric, int k, int32_t* out_idx_dev /*[Q, k]*/,
                double* out_dist_dev /*[Q, k]*/, void* workspace_dev, size_t workspace_bytes, int mode,
                mrb200_stream_t stream);
+/* r-disc search on the tensor-core candidate generator (euclidean / max_euclidean, N >= 1024): coarse TF32 distances
+ * select, per query row, every point that can lie within the radius (at most `cap` of them); an exact fp64 pass in the
+ * reference's operand order keeps those that do (d < r, or d <= r + 1e-10 when inclusive) in ascending index order.
+ * count: counts_dev[Q] = neighbours of the row, or -1 if its candidates exceeded `cap` (answer that row with
+ * mrb200_radius_count / _fill).  The caller scans the counts into offsets (rows with -1 take their exact count), then
+ * fill writes out_idx / out_dist (nullable) for the rows that did not overflow.  Same workspace for both calls. */
+size_t mrb200_radius_tc_workspace_bytes(int64_t Q, int64_t N, int D, int cap);
+int mrb200_radius_tc_count(const double* queries_dev, const double* corpus_dev, int64_t Q, int64_t N, int D,
+                           const int32_t* slices_host, int R, int metric, const double* radii_dev, double radius, int inclusive,
+                           int cap, void* workspace_dev, size_t workspace_bytes, int64_t* counts_dev, mrb200_stream_t stream);
+int mrb200_radius_tc_fill(const double* queries_dev, const double* corpus_dev, int64_t Q, int64_t N, int D,
+                          const int32_t* slices_host, int R, int metric, int cap, void* workspace_dev, size_t workspace_bytes,
+                          const int64_t* offsets_dev, int32_t* out_idx_dev, double* out_dist_dev, mrb200_stream_t stream);
 /* radius search in two launches around a caller-side exclusive scan.  splits =
  * mrb200_radius_splits(Q, N) corpus ranges are searched independently; counts_dev is [Q * splits]
  * (row major).  radii_dev (per query) nullable, then `radius` applies to all.  inclusive = 0:

@@ -53,6 +53,11 @@ SIGNATURES = {
     "mrb200_knn_stats_offset": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "mrb200_knn": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp,
                              C.c_size_t, C.c_int, c_vp]),
+    "mrb200_radius_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "mrb200_radius_tc_count": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, c_vp, C.c_double, C.c_int,
+                                         C.c_int, c_vp, C.c_size_t, c_vp, c_vp]),
+    "mrb200_radius_tc_fill": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, c_vp, C.c_size_t,
+                                        c_vp, c_vp, c_vp, c_vp]),
     "mrb200_radius_splits": (C.c_int, [C.c_int64, C.c_int64]),
     "mrb200_radius_count": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, c_vp, C.c_double,
                                       C.c_int, C.c_int, c_vp, c_vp]),

@@ -412,8 +412,11 @@ static int check_configs_impl(const mrb200_scene_t* sc, int slot, const float* q
         // (several host threads may query one handle: the state is a relaxed atomic; a lost race only repeats the decision)
         int state = __atomic_load_n(&s->two_phase_state, __ATOMIC_RELAXED);
         if (state == 0 && !s->two_phase_forced) {
-            const volatile int* st2 = sc->stats_pin + 2 * slot;
-            const int seen = st2[0], decided = st2[1];
+            // (seen, decided) land together as one 8-byte copy behind every measuring launch; read them with ONE 64-bit
+            // load: two 4-byte reads could pair the `seen` of an older copy with the `decided` of a newer one and settle
+            // the slot on the wrong kernel (seen in round 2: the dual-arm headline ran two-phase tiles, 3.0 instead of 2.7 ms)
+            const uint64_t both = __atomic_load_n(reinterpret_cast<const uint64_t*>(sc->stats_pin + 2 * slot), __ATOMIC_RELAXED);
+            const int seen = (int)(uint32_t)both, decided = (int)(uint32_t)(both >> 32);
             if (seen >= 4096) {
                 state = (int64_t)decided * 20 >= (int64_t)seen * 11 ? 1 : 2;
                 __atomic_store_n(&s->two_phase_state, state, __ATOMIC_RELAXED);
@@ -771,6 +774,55 @@ int mrb200_knn(const double* queries, const double* corpus, int64_t Q, int64_t N
     cudaError_t e = mrb::launch_knn_exact(queries, corpus, Q, N, D, sl, metric, k, splits, part_d, part_i, out_idx, out_dist, nullptr, st);
     if (e != cudaSuccess) return cuda_fail(e, "knn");
     g_launches += 2;
+    return MRB200_OK;
+}
+
+// ---- r-disc search on the tensor-core candidate generator ----
+static bool radius_tc_plan(int64_t Q, int64_t N, int D, const mrb::Slices& sl, int metric, mrb::TcPlan* plan) {
+    if (N < 1024 || Q < 1) return false;
+    if (!mrb::knn_tc_make_plan(D, sl, metric, plan)) return false;
+    return mrb::knn_tc_smem_bytes(*plan, 0) <= 224 * 1024;
+}
+
+size_t mrb200_radius_tc_workspace_bytes(int64_t Q, int64_t N, int D, int cap) {
+    if (Q <= 0 || cap <= 0) return 256;
+    const int ks = (D + 2 + 7) / 8 + 8;   // worst plan, as for mrb200_knn_workspace_bytes
+    return 256 + align256((size_t)((Q + 127) / 128) * ks * 128 * 32) + align256((size_t)(N + 256) * ks * 32) + align256((size_t)Q * 4 + 16) +
+           align256((size_t)Q * (size_t)cap * 4) + 4096;
+}
+
+int mrb200_radius_tc_count(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const int32_t* slices_host, int R,
+                           int metric, const double* radii, double radius, int inclusive, int cap, void* workspace, size_t workspace_bytes,
+                           int64_t* counts, mrb200_stream_t stream) {
+    mrb::Slices sl;
+    if (int rc = make_slices(slices_host, R, D, metric, &sl)) return rc;
+    if (Q < 0 || N < 0 || cap < 1 || (Q && (!queries || !counts)) || (N && !corpus)) return fail(MRB200_ERR_ARG, "radius_tc_count: bad argument");
+    if (Q == 0) return MRB200_OK;
+    mrb::TcPlan plan;
+    if (!radius_tc_plan(Q, N, D, sl, metric, &plan))
+        return fail(MRB200_ERR_ARG, "radius_tc_count: the tensor-core path needs metric euclidean / max_euclidean and N >= 1024");
+    if (!workspace || workspace_bytes < mrb200_radius_tc_workspace_bytes(Q, N, D, cap)) return fail(MRB200_ERR_ARG, "radius_tc_count: workspace too small");
+    cudaError_t e = mrb::launch_radius_tc_count(queries, corpus, Q, N, D, sl, metric, radii, radius, inclusive, cap, plan, workspace, counts,
+                                                (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "radius_tc_count");
+    g_launches += 4;
+    return MRB200_OK;
+}
+
+int mrb200_radius_tc_fill(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const int32_t* slices_host, int R,
+                          int metric, int cap, void* workspace, size_t workspace_bytes, const int64_t* offsets, int32_t* out_idx,
+                          double* out_dist, mrb200_stream_t stream) {
+    mrb::Slices sl;
+    if (int rc = make_slices(slices_host, R, D, metric, &sl)) return rc;
+    if (Q < 0 || (Q && (!queries || !offsets || !out_idx || !workspace))) return fail(MRB200_ERR_ARG, "radius_tc_fill: bad argument");
+    if (Q == 0) return MRB200_OK;
+    mrb::TcPlan plan;
+    if (!radius_tc_plan(Q, N, D, sl, metric, &plan)) return fail(MRB200_ERR_ARG, "radius_tc_fill: unsupported metric / size");
+    if (workspace_bytes < mrb200_radius_tc_workspace_bytes(Q, N, D, cap)) return fail(MRB200_ERR_ARG, "radius_tc_fill: workspace too small");
+    cudaError_t e = mrb::launch_radius_tc_fill(queries, corpus, Q, N, D, sl, metric, cap, plan, workspace, offsets, out_idx, out_dist,
+                                               (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "radius_tc_fill");
+    g_launches++;
     return MRB200_OK;
 }
 

@@ -88,6 +88,13 @@ size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, 
 cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
                           int k, int kc, const TcPlan& plan, int splits, void* workspace, int32_t* out_idx, double* out_dist,
                           uint8_t* certified, cudaStream_t st);
+size_t radius_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int cap);
+cudaError_t launch_radius_tc_count(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
+                                   const double* radii, double radius, int inclusive, int cap, const TcPlan& plan, void* workspace,
+                                   int64_t* counts, cudaStream_t st);
+cudaError_t launch_radius_tc_fill(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
+                                  int cap, const TcPlan& plan, void* workspace, const int64_t* offsets, int32_t* out_idx, double* out_dist,
+                                  cudaStream_t st);
 cudaError_t launch_radius(bool fill, const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl,
                           int metric, const double* radii, double radius, int inclusive, int splits, int64_t* counts,
                           const int64_t* offsets, int32_t* out_idx, double* out_dist, cudaStream_t st);

@@ -118,31 +118,18 @@ def batch_knn(queries: torch.Tensor, corpus: torch.Tensor, slices=None, metric: 
     return (idx, dist) if return_dist else idx
 
 
-def batch_radius(queries: torch.Tensor, corpus: torch.Tensor, radius: Union[float, torch.Tensor], slices=None,
-                 metric: str = "max_euclidean", inclusive: bool = False, return_dist: bool = False):
-    """Radius neighbours in CSR form, indices ascending per row (the reference's np.where order).
-    inclusive=False: d < r (PRM, prm_graph.py:500); True: d <= r + 1e-10 (RRT*/IT*).
-    -> (offsets [Q+1] int64, indices int32 [, dists float64])"""
+def _radius_exact(queries, corpus, radius, radii, slices, metric, inclusive, return_dist):
     lib = _lib.load()
-    queries, corpus = _f64(queries, "queries"), _f64(corpus, "corpus")
     Q, D = queries.shape
     N = corpus.shape[0]
     s, R = _slices(slices)
     sp = s.ctypes.data_as(_lib.c_i32p) if s is not None else None
     dev = queries.device
-    radii = None
-    r = 0.0
-    if isinstance(radius, torch.Tensor):
-        radii = _f64(radius.reshape(-1), "radius")
-        if radii.numel() != Q:
-            raise ValueError("one radius per query expected")
-    else:
-        r = float(radius)
     with torch.cuda.device(dev):
         splits = int(lib.mrb200_radius_splits(Q, N))
         counts = torch.zeros(Q * splits, dtype=torch.int64, device=dev)
         args = (queries.data_ptr(), corpus.data_ptr(), Q, N, D, sp, R, METRICS[metric],
-                radii.data_ptr() if radii is not None else None, r, int(inclusive), splits)
+                radii.data_ptr() if radii is not None else None, radius, int(inclusive), splits)
         _lib.check(lib.mrb200_radius_count(*args, counts.data_ptr(), _stream(dev)), "radius_count")
         ends = torch.cumsum(counts, 0)           # plumbing: the scan between the two launches
         offs = ends - counts
@@ -153,4 +140,72 @@ def batch_radius(queries: torch.Tensor, corpus: torch.Tensor, radius: Union[floa
             _lib.check(lib.mrb200_radius_fill(*args, offs.data_ptr(), idx.data_ptr(), dist.data_ptr() if dist is not None else None,
                                               _stream(dev)), "radius_fill")
         row_off = torch.cat([offs.view(Q, splits)[:, 0], ends[-1:]]) if Q else torch.zeros(1, dtype=torch.int64, device=dev)
+    return row_off, idx, dist
+
+
+def batch_radius(queries: torch.Tensor, corpus: torch.Tensor, radius: Union[float, torch.Tensor], slices=None,
+                 metric: str = "max_euclidean", inclusive: bool = False, return_dist: bool = False, mode: str = "auto",
+                 cap: int = 512):
+    """Radius neighbours in CSR form, indices ascending per row (the reference's np.where order).
+    inclusive=False: d < r (PRM, prm_graph.py:500); True: d <= r + 1e-10 (RRT*/IT*).
+    mode: "exact" = fp64 CUDA-core kernels; "tensor" = tcgen05 candidate generator + exact fp64 filter (euclidean /
+    max_euclidean, at most `cap` candidates per row, rows beyond that are answered by the exact kernels); "auto" picks the
+    tensor path for large selective searches.  Both return identical results.
+    -> (offsets [Q+1] int64, indices int32 [, dists float64])"""
+    lib = _lib.load()
+    queries, corpus = _f64(queries, "queries"), _f64(corpus, "corpus")
+    Q, D = queries.shape
+    N = corpus.shape[0]
+    dev = queries.device
+    radii = None
+    r = 0.0
+    if isinstance(radius, torch.Tensor):
+        radii = _f64(radius.reshape(-1), "radius")
+        if radii.numel() != Q:
+            raise ValueError("one radius per query expected")
+    else:
+        r = float(radius)
+    tensor_ok = metric in ("euclidean", "max_euclidean") and N >= 1024 and Q >= 1
+    if mode == "tensor" and not tensor_ok:
+        raise ValueError("the tensor-core radius path needs metric euclidean / max_euclidean and N >= 1024")
+    use_tensor = mode == "tensor" or (mode == "auto" and tensor_ok and Q >= 256 and N >= 4096)
+    if not use_tensor:
+        off, idx, dist = _radius_exact(queries, corpus, r, radii, slices, metric, inclusive, return_dist)
+        return (off, idx, dist) if return_dist else (off, idx)
+    s, R = _slices(slices)
+    sp = s.ctypes.data_as(_lib.c_i32p) if s is not None else None
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.mrb200_radius_tc_workspace_bytes(Q, N, D, cap))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        counts = torch.empty(Q, dtype=torch.int64, device=dev)
+        _lib.check(lib.mrb200_radius_tc_count(queries.data_ptr(), corpus.data_ptr(), Q, N, D, sp, R, METRICS[metric],
+                                              radii.data_ptr() if radii is not None else None, r, int(inclusive), int(cap),
+                                              ws.data_ptr(), ws_bytes, counts.data_ptr(), _stream(dev)), "radius_tc_count")
+        over = torch.nonzero(counts < 0).flatten()        # rows with more than `cap` candidates
+        n_over = int(over.numel())
+        if mode == "auto" and n_over > Q // 4:             # a radius this wide is not a candidate-list problem
+            off, idx, dist = _radius_exact(queries, corpus, r, radii, slices, metric, inclusive, return_dist)
+            return (off, idx, dist) if return_dist else (off, idx)
+        ex = None
+        if n_over:   # plumbing: the exact kernels answer the overflowed rows, their results are spliced in below
+            ex = _radius_exact(queries[over].contiguous(), corpus, r, None if radii is None else radii[over].contiguous(), slices, metric,
+                               inclusive, return_dist)
+            counts[over] = ex[0][1:] - ex[0][:-1]
+        ends = torch.cumsum(counts, 0)
+        offs = (ends - counts).contiguous()
+        total = int(ends[-1].item())
+        idx = torch.empty(total, dtype=torch.int32, device=dev)
+        dist = torch.empty(total, dtype=torch.float64, device=dev) if return_dist else None
+        if total:
+            _lib.check(lib.mrb200_radius_tc_fill(queries.data_ptr(), corpus.data_ptr(), Q, N, D, sp, R, METRICS[metric], int(cap),
+                                                 ws.data_ptr(), ws_bytes, offs.data_ptr(), idx.data_ptr(),
+                                                 dist.data_ptr() if dist is not None else None, _stream(dev)), "radius_tc_fill")
+        if n_over:
+            lens = ex[0][1:] - ex[0][:-1]
+            dst = torch.repeat_interleave(offs[over], lens) + (torch.arange(int(ex[0][-1].item()), device=dev) -
+                                                              torch.repeat_interleave(ex[0][:-1], lens))
+            idx[dst] = ex[1]
+            if dist is not None:
+                dist[dst] = ex[2]
+        row_off = torch.cat([offs, ends[-1:]])
     return (row_off, idx, dist) if return_dist else (row_off, idx)

