@@ -445,7 +445,19 @@ if HAVE_REFERENCE:
         def config_cost(self, start, end) -> float:
             return config_cost(start, end, self.cost_metric, self.cost_reduction)
 
+        DEVICE_COST_MIN_ROWS = 32768   # below this the reference's own numba kernel beats a device round trip
+
         def batch_config_cost(self, starts, ends, tmp_agent_slice=None):
+            if (tmp_agent_slice is None and isinstance(ends, np.ndarray) and ends.ndim == 2 and len(ends) >= self.DEVICE_COST_MIN_ROWS
+                    and hasattr(starts, "state") and hasattr(self.model.device, "dev")):
+                # one-to-many cost over a large array (informed-set tests over whole sample batches): mrb200_batch_cost
+                import torch
+                from . import knn as K
+                dev = self.model.device.dev
+                sl = [[self.robot_idx[r][0], self.robot_idx[r][-1] + 1] for r in self.robots]
+                a = torch.from_numpy(np.ascontiguousarray(starts.state(), np.float64)).to(dev)
+                b = torch.from_numpy(np.ascontiguousarray(ends, np.float64)).to(dev)
+                return K.batch_config_cost(a, b, sl, self.cost_metric, self.cost_reduction).cpu().numpy()
             costs = batch_config_cost(starts, ends, self.cost_metric, self.cost_reduction, tmp_agent_slice=tmp_agent_slice)
             # candidate-edge speculation (SpeculativeCache): the PRM search asks for the edge costs from the node it has
             # just reached to all of its neighbours (prm_graph.py:706-712) -- those are the edges it may check next

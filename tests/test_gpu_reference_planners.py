@@ -135,3 +135,19 @@ def test_reference_planners_solve_b200_scenes_on_the_device(envmod, env_name, pl
         if not twin.is_edge_collision_free(s0.q, s1.q, m):
             bad += 1
     assert bad <= 1, f"{bad} path edges the oracle rejects"
+
+
+def test_env_batch_cost_routes_large_arrays_to_the_device(envmod):
+    """B200Env.batch_config_cost uses mrb200_batch_cost above a size threshold; values equal the
+    reference's numba kernel (configuration.py:437-510) to 1 ulp, for both cost reductions"""
+    from multi_robot_multi_goal_planning.problems.core.configuration import batch_config_cost
+    env = envmod.b200_box_rearrangement(speculate=False)
+    rng = np.random.RandomState(0)
+    pts = rng.uniform(env.limits[0], env.limits[1], (env.DEVICE_COST_MIN_ROWS + 17, env.limits.shape[1]))
+    for red in ("max", "sum"):
+        env.cost_reduction = red
+        got = env.batch_config_cost(env.start_pos, pts)
+        want = batch_config_cost(env.start_pos, pts, env.cost_metric, red)
+        assert got.shape == want.shape and np.allclose(got, want, rtol=4e-16, atol=0)
+    small = env.batch_config_cost(env.start_pos, pts[:100])
+    assert np.array_equal(small, batch_config_cost(env.start_pos, pts[:100], env.cost_metric, env.cost_reduction))
