@@ -84,6 +84,42 @@ int main(int argc, char** argv) {
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&ms, e0, e1);
     printf("edges:   %ld, %.3f ms per launch, %.4g edge checks/s\n", E, ms / reps, E * (double)reps / (ms * 1e-3));
+
+    // planner-like local edges: free start configurations, every joint moves by at most +-0.2 (clamped to the limits)
+    {
+        std::vector<float> a, b;
+        std::mt19937 r2(1);
+        const long want = 131072;
+        for (long i = 0; i < B && (long)a.size() < want * D; i++) {
+            if (!flags[i]) continue;
+            for (int k = 0; k < D; k++) {
+                const float x = q[i * D + k];
+                float y = x + std::uniform_real_distribution<float>(-0.2f, 0.2f)(r2);
+                y = y < lim[k] ? lim[k] : (y > lim[D + k] ? lim[D + k] : y);
+                a.push_back(x);
+                b.push_back(y);
+            }
+        }
+        const long El = (long)a.size() / D;
+        if (El > 0) {
+            float *da, *db;
+            int* dfirst2;
+            cudaMalloc(&dfirst2, El * 4);
+            cudaMalloc(&da, a.size() * 4);
+            cudaMalloc(&db, b.size() * 4);
+            cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice);
+            for (int i = 0; i < 2; i++)
+                CK(mrb200_check_edges(scene, 0, da, db, El, 0.01, nullptr, 0, -1, 0, -1.f, dflags, dfirst2, nullptr));
+            cudaEventRecord(e0);
+            for (int i = 0; i < reps; i++)
+                CK(mrb200_check_edges(scene, 0, da, db, El, 0.01, nullptr, 0, -1, 0, -1.f, dflags, dfirst2, nullptr));
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+            printf("local:   %ld, %.3f ms per launch, %.4g edge checks/s\n", El, ms / reps, El * (double)reps / (ms * 1e-3));
+        }
+    }
     mrb200_scene_destroy(scene);
     return 0;
 }
