@@ -352,6 +352,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one rank per GPU: run on the CPUs (and, by first touch, allocate the pinned staging memory) of the GPU's NUMA node
+    from multirobot_pathplanning_benchmark_b200.dist import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else {"bound": False, "note": "single rank: not bound"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -554,7 +557,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": world * B * D * 4,
                 "d2h_bytes_per_step": world * B, "steps": e2e_steps, "timing": "CUDA events on the calling stream (which waits for the copy streams) around "
                 "calls that return after the flags have landed in host memory, max over ranks",
-                "h2d_only_gbs_per_rank_min": h2d_gbs_min, "h2d_needed_gbs_per_rank_at_value": value / world * D * 4 / 1e9,
+                "h2d_only_gbs_per_rank_min": h2d_gbs_min, "numa": numa, "h2d_needed_gbs_per_rank_at_value": value / world * D * 4 / 1e9,
                 "path": "pinned host -> H2D -> check_configs -> D2H, 512k-config chunks on 2 streams"},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
     }

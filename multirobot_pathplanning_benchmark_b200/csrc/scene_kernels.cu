@@ -480,35 +480,6 @@ __device__ __noinline__ void run_queued_types(const TileArgs args, int warp, boo
             for (int base = lo; base < hi; base += 32) {
                 const int cnt = min(32, hi - base);
                 uint32_t mask = 0u;
-#ifdef MRB_PAD4
-                // sublists 0 and 1 are padded (scene.py) to a multiple of 16 records with records that never pass, so every
-                // warp's share is a whole number of groups of four: no remainder loop in the instruction stream
-                if (sub == 0) {
-                    for (int j0 = 0; j0 < cnt; j0 += 4) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = j0 + u;
-                            const uint2 r = rec[base + j];
-                            const float* px = reinterpret_cast<const float*>(Wl + (r.x & 0xffffu));
-                            const float* py = reinterpret_cast<const float*>(Wl + (r.x >> 16));
-                            const float x = px[0] - py[0], y = px[TILE] - py[TILE], z = px[2 * TILE] - py[2 * TILE];
-                            mask |= (dot3(x, y, z, x, y, z) < __uint_as_float(r.y) ? 1u : 0u) << j;
-                        }
-                    }
-                } else if (sub == 1) {
-                    for (int j0 = 0; j0 < cnt; j0 += 4) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = j0 + u;
-                            const uint2 r = rec[base + j];
-                            const float* px = reinterpret_cast<const float*>(Wl + (r.x & 0xffffu));
-                            const float4 cb = scentre[r.x >> 16];
-                            const float x = px[0] - cb.x, y = px[TILE] - cb.y, z = px[2 * TILE] - cb.z;
-                            mask |= (dot3(x, y, z, x, y, z) < __uint_as_float(r.y) ? 1u : 0u) << j;
-                        }
-                    }
-                }
-#else
                 if (sub == 0) {  // partner moving: bounding spheres (branch-free body: independent iterations overlap)
 #pragma unroll 4
                     for (int j = 0; j < cnt; ++j) {
@@ -528,7 +499,6 @@ __device__ __noinline__ void run_queued_types(const TileArgs args, int warp, boo
                         mask |= (dot3(x, y, z, x, y, z) < __uint_as_float(r.y) ? 1u : 0u) << j;
                     }
                 }
-#endif
                 else {  // partner is a large static box: separating-axis bound along its face normals
                     for (int j = 0; j < cnt; ++j) {
                         const uint2 r = rec[base + j];
@@ -724,13 +694,7 @@ __device__ __noinline__ float full_tile_call(int blob_words, int D, int world_wo
 // MINB: CTAs per SM the register allocation has to allow.  16 resident warps by default; scenes whose shared-memory
 // footprint admits only three 4-warp CTAs anyway (four-arm scene: 65 KB) get the variant compiled for three, i.e. up
 // to 168 registers per thread instead of 128.
-#ifndef MRB_MINB2
-#define MRB_MINB2 8          // resident 2-warp CTAs per SM the register allocation has to allow (16 warps)
-#endif
-#ifndef MRB_EDGE_FKCALL
-#define MRB_EDGE_FKCALL false
-#endif
-template <int WARPS, bool TWO_PHASE, int MINB = (WARPS == 2 ? MRB_MINB2 : 16 / WARPS)>
+template <int WARPS, bool TWO_PHASE, int MINB = 16 / WARPS>
 __global__ void __launch_bounds__(TILE * WARPS, MINB) check_configs_kernel(ConfigParams p) {
     constexpr int THREADS = TILE * WARPS;
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, TWO_PHASE ? 2 : 0);
@@ -899,7 +863,7 @@ __global__ void __launch_bounds__(TILE * WARPS, MINB) check_configs_kernel(Confi
 // when its window is exhausted, and its slot is refilled from the dynamic edge counter.
 // ------------------------------------------------------------------------------------------
 template <int WARPS>
-__global__ void __launch_bounds__(TILE * WARPS, (WARPS == 2 ? MRB_MINB2 : 16 / WARPS)) check_edges_kernel(EdgeParams p) {
+__global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(EdgeParams p) {
     constexpr int THREADS = TILE * WARPS;
     constexpr int K = EDGE_SLOTS;
     const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, true);
@@ -1031,7 +995,7 @@ __global__ void __launch_bounds__(TILE * WARPS, (WARPS == 2 ? MRB_MINB2 : 16 / W
         bool relpen;
         // full evaluation of every sample: stopping the decided samples early (as the configuration kernel does) gains
         // 2-13 % on long uniform edges and loses 1-3 % on the short edges planners actually check (measured)
-        const float total_pen = process_tile<WARPS, MRB_EDGE_FKCALL>(sm, sm.q[0], D, tol, false, false, &relpen);
+        const float total_pen = process_tile<WARPS>(sm, sm.q[0], D, tol, false, false, &relpen);
         if (warp == 0) {
             const unsigned hit = __ballot_sync(FULL, s_idx[lane] >= 0 && total_pen > tol);
             if (lane < K && s_take[lane] > 0) {

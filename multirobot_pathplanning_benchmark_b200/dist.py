@@ -72,3 +72,42 @@ def gather_csr(offsets: torch.Tensor, indices: torch.Tensor, n_rows_total: int, 
     all_off = torch.zeros(n_rows_total + 1, dtype=torch.int64, device=offsets.device)
     all_off[1:] = torch.cumsum(all_counts, 0)
     return all_off, all_idx
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pins this process (one rank per GPU) to the CPUs of the NUMA node its GPU hangs on, BEFORE the rank allocates its
+    pinned host buffers: first-touch then places them in that node's memory, and the H2D copies of the host-buffer API
+    (backend.check_configs_host) stay off the inter-socket link.  Round 1 measured the end-to-end rate at 0.45 of linear
+    on 8 GPUs with every rank's staging memory wherever the launcher happened to run.
+    -> what was done ({"numa_node", "cpus", "bound"}); never raises (containers may hide sysfs or forbid affinity)."""
+    import os
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        cpus = _parse_cpulist(open(f"{base}/local_cpulist").read())
+        info["numa_node"] = node
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        info["cpus"] = len(cpus)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+    except Exception as e:   # noqa: BLE001 -- report, do not fail the run
+        info["error"] = repr(e)[:120]
+    return info

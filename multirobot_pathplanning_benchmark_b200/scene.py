@@ -427,7 +427,6 @@ H_N_PAIRS = 28     # [28..35]
 H_OFF_SHAPE_ROBOT = 36
 H_OFF_SCENTRE = 37   # static shape centres, 4 floats each
 H_BP = 48            # broadphase sublists: [type][sublist] -> (record offset, count), 8 x 3 x 2 words
-BP_PAD = 16          # bounding-sphere sublists are padded to a multiple of this many records
 BP_SUBLISTS = 3      # 0: partner moving (bounding spheres), 1: partner static (bounding spheres),
                      # 2: partner is a large static box (face-normal separating-axis bound)
 STAGE_IDS_MAX_BYTES = 12 * 1024   # blobs whose staged prefix stays below this keep the records' pair ids in it
@@ -685,13 +684,6 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
                 bp[t][1].append((wbytes(x) | ((y - n_mov) << 16), (bound_rs[x] + bound_rs[y] + CULL_SLACK) ** 2, packed))
         for sl in bp[t]:
             sl.sort(key=lambda r: (r[0] & 0xffff, r[0] >> 16))
-        # bounding-sphere sublists are padded to a multiple of 16 records with records that can never pass (negative
-        # threshold against a squared distance), so that every warp's share is a whole number of groups of four and the
-        # kernels' unrolled test loops need no remainder code
-        for k in (0, 1):
-            sl = bp[t][k]
-            while sl and len(sl) % BP_PAD:
-                sl.append((sl[-1][0], -1.0, 0))
 
     # --- assemble words ---
     # staged prefix (copied into shared memory by every CTA): header, frames, shapes, chains, the pair lists of the

@@ -75,12 +75,7 @@ def test_every_record_names_a_pair_of_its_type(compiled):
         for k in range(S.BP_SUBLISTS):
             off, m = b[S.H_BP + (t * S.BP_SUBLISTS + k) * 2], b[S.H_BP + (t * S.BP_SUBLISTS + k) * 2 + 1]
             ids = b[S.H_BP_IDS + t * S.BP_SUBLISTS + k]
-            if k < 2:
-                assert m % S.BP_PAD == 0       # bounding-sphere sublists are padded for the kernels' unrolled loops
             for i in range(m):
-                if cs.blob32[off + 2 * i + 1:off + 2 * i + 2].view(np.float32)[0] < 0:
-                    assert k < 2               # padding record: negative threshold against a squared distance
-                    continue
                 pk = int(b[ids + i])
                 a, c = pk & 0xffff, (pk >> 16) & 0xfff
                 assert (a, c) in listed and (a, c) not in seen

@@ -16,8 +16,6 @@ def _records(cs):
         for k in range(S.BP_SUBLISTS):
             off, n = int(b[S.H_BP + (t * S.BP_SUBLISTS + k) * 2]), int(b[S.H_BP + (t * S.BP_SUBLISTS + k) * 2 + 1])
             for i in range(n):
-                if b[off + 2 * i + 1:off + 2 * i + 2].view(np.float64)[0] < 0:
-                    continue   # padding record (negative threshold: never passes), see scene.py BP_PAD
                 pk = int(b[int(b[S.H_IDS_BASE]) + (off - int(b[S.H_REC_BASE])) // 2 + i])
                 out.add((pk & 0xffff, (pk >> 16) & 0xfff))
     return out
