@@ -498,8 +498,7 @@ __device__ __noinline__ void run_queued_types(const TileArgs args, int warp, boo
                         const float x = px[0] - cb.x, y = px[TILE] - cb.y, z = px[2 * TILE] - cb.z;
                         mask |= (dot3(x, y, z, x, y, z) < __uint_as_float(r.y) ? 1u : 0u) << j;
                     }
-                }
-                else {  // partner is a large static box: separating-axis bound along its face normals
+                } else {  // partner is a large static box: separating-axis bound along its face normals
                     for (int j = 0; j < cnt; ++j) {
                         const uint2 r = rec[base + j];
                         const unsigned xo = r.x & 0xffffu;

@@ -763,6 +763,34 @@ if HAVE_REFERENCE:
             self.set_to_mode(mode)
             return self.model.sample_informed(self._slot, n, focal_points, cost_bound, self.cost_metric, self.cost_reduction, rng)
 
+        # ---- distances / neighbours (numpy or CUDA tensors in; see neighbours.py for the planners' own call) ----
+        def _slices(self):
+            return [[self.robot_idx[r][0], self.robot_idx[r][-1] + 1] for r in self.robots]
+
+        def _f64(self, a):
+            import torch
+            if isinstance(a, torch.Tensor):
+                return a
+            return torch.from_numpy(np.ascontiguousarray(a, np.float64)).to(self.model.device.dev)
+
+        def batch_config_dist(self, q, pts, metric: str = "max"):
+            """one-to-many distance on the device (P/problems/core/configuration.py:303-349), numpy [N] float64"""
+            from . import knn as K
+            qs = q.state() if hasattr(q, "state") else q
+            return K.batch_config_dist(self._f64(qs), self._f64(pts), self._slices(), metric).cpu().numpy()
+
+        def batch_knn(self, queries, corpus, k: int, metric: str = "max_euclidean", mode: str = "auto"):
+            """k nearest corpus rows of every query row -> (idx [Q, k] int32, dist [Q, k] float64) device tensors;
+            the reference's selection (P/planners/prm/prm_graph.py:440-447) for whole batches"""
+            from . import knn as K
+            return K.batch_knn(self._f64(queries), self._f64(corpus), self._slices(), metric, k, mode=mode)
+
+        def batch_radius(self, queries, corpus, radius, metric: str = "max_euclidean", inclusive: bool = False, mode: str = "auto"):
+            """r-disc neighbours in CSR form (offsets [Q + 1], indices), ascending indices per row
+            (prm_graph.py:479-538: d < r; rrtstar_base.py / itstar_base.py: d <= r + 1e-10 with inclusive=True)"""
+            from . import knn as K
+            return K.batch_radius(self._f64(queries), self._f64(corpus), radius, self._slices(), metric, inclusive=inclusive, mode=mode)
+
         # ---- additive batch variants (arrays or CUDA tensors in, device tensors out) -----------
         def batch_is_collision_free(self, qs, mode):
             self.set_to_mode(mode)
