@@ -154,6 +154,14 @@ int mrb200_batch_dist(const double* q_dev /*[D]*/, const double* pts_dev /*[N, D
 int mrb200_batch_cost(const double* a_dev, int a_is_single, const double* b_dev /*[N, D]*/, int64_t N, int D,
                       const int32_t* slices_host, int R, int per_robot_max, int reduction_sum, double w,
                       double* out_dev /*[N]*/, mrb200_stream_t stream);
+/* One relaxation step of the lower bound on the cost to the goal (compute_lower_bound_to_goal,
+ * P/planners/prm/prm_graph.py:143-220, relaxes transition nodes one at a time with batch_config_cost): for the exit
+ * configurations a[T1, D] of one mode and those of the modes it leads into, b[T2, D] with their bounds lb_b[T2],
+ *     out[i] = min_j ( cost(a_i, b_j) + lb_b[j] ),   arg[i] = the minimising j (smallest on ties; nullable; -1 if T2 = 0)
+ * with the cost of mrb200_batch_cost (per-robot euclidean or max-abs, reduced by sum or by max + w * sum). */
+int mrb200_minplus_cost(const double* a_dev, int64_t T1, const double* b_dev, const double* lb_b_dev, int64_t T2, int D,
+                        const int32_t* slices_host, int R, int per_robot_max, int reduction_sum, double w, double* out_dev,
+                        int32_t* arg_dev, mrb200_stream_t stream);
 /* k nearest neighbours of every query row, ascending (distance, index); rows with fewer than k
  * corpus points are padded with index -1 / distance +inf.  out_dist_dev nullable.  The workspace
  * (device, mrb200_knn_workspace_bytes) is scratch for partial results.

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmrb200.so")
+# (MRB200_LIB: an experiment build of the same library, scripts/build_variant.sh; never a different implementation)
+LIB_PATH = os.environ.get("MRB200_LIB") or os.path.join(HERE, "libmrb200.so")
 
 _lib = None
 
@@ -49,6 +50,8 @@ SIGNATURES = {
     "mrb200_batch_dist": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, c_vp, c_vp]),
     "mrb200_batch_cost": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, C.c_double, c_vp,
                                     c_vp]),
+    "mrb200_minplus_cost": (C.c_int, [c_vp, C.c_int64, c_vp, c_vp, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, C.c_double, c_vp,
+                                      c_vp, c_vp]),
     "mrb200_knn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "mrb200_knn_stats_offset": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "mrb200_knn": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp,

@@ -712,6 +712,18 @@ int mrb200_batch_cost(const double* a, int a_is_single, const double* b, int64_t
     return MRB200_OK;
 }
 
+int mrb200_minplus_cost(const double* a, int64_t T1, const double* b, const double* lb_b, int64_t T2, int D, const int32_t* slices_host,
+                        int R, int per_robot_max, int reduction_sum, double w, double* out_dev, int32_t* arg_dev, mrb200_stream_t stream) {
+    mrb::Slices sl;
+    if (int rc = make_slices(slices_host, R, D, MRB200_METRIC_MAX_EUCLIDEAN, &sl)) return rc;
+    if (T1 < 0 || T2 < 0 || (T1 && (!a || !out_dev)) || (T2 && (!b || !lb_b))) return fail(MRB200_ERR_ARG, "minplus_cost: bad argument");
+    if (T1 == 0) return MRB200_OK;
+    cudaError_t e = mrb::launch_minplus_cost(a, T1, b, lb_b, T2, D, sl, per_robot_max, reduction_sum, w, out_dev, arg_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "minplus_cost");
+    g_launches++;
+    return MRB200_OK;
+}
+
 static int tc_max_splits(int64_t Q) {   // upper bound of knn_tc_splits for any corpus
     const int64_t qt = (Q + 127) / 128;
     int64_t s = (160 + qt - 1) / qt;
@@ -722,7 +734,7 @@ static size_t tc_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
     // sized for the worst plan: K steps of the euclidean plan + one per robot (<= 8 accumulators), the narrowest tile
     const int ks = (D + 2 + 7) / 8 + 8;
     const int splits = tc_max_splits(Q);
-    const size_t lists = (size_t)splits * 2;
+    const size_t lists = (size_t)splits * mrb::knn_tc_parts();
     return 256 + align256((size_t)((Q + 127) / 128) * ks * 128 * 32) + align256((size_t)(N + 256) * ks * 32) +
            align256(lists * (size_t)Q * ((size_t)(k + 16) * 8 + 4)) + align256((size_t)Q * 4 + 16) + align256((size_t)1024 * 32 * (size_t)k * 12) + align256((size_t)Q) + 4096;
 }
@@ -762,7 +774,7 @@ int mrb200_knn(const double* queries, const double* corpus, int64_t Q, int64_t N
     if (use_tc) {
         const int64_t ct = (N + plan.tn - 1) / plan.tn;
         const int tsplits = mrb::knn_tc_splits(Q, ct);
-        const int kc = mrb::knn_tc_slots(k, 2 * tsplits);   // output slots per row and list
+        const int kc = mrb::knn_tc_slots(k, mrb::knn_tc_parts() * tsplits);   // output slots per row and list
         uint8_t* certified = tc_ws;
         cudaError_t e = mrb::launch_knn_tc(queries, corpus, Q, N, D, sl, metric, k, kc, plan, tsplits, tc_ws + align256((size_t)Q), out_idx,
                                            out_dist, certified, st);

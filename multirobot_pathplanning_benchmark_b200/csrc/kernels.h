@@ -76,6 +76,8 @@ cudaError_t launch_knn_exact(const double* queries, const double* corpus, int64_
                              cudaStream_t st);
 cudaError_t launch_batch_cost(const double* a, int64_t a_stride, const double* b, int64_t N, int D, const Slices& sl, int per_robot_max,
                               int reduction_sum, double w, double* out, cudaStream_t st);
+cudaError_t launch_minplus_cost(const double* a, int64_t T1, const double* b, const double* lb_b, int64_t T2, int D, const Slices& sl,
+                                int per_robot_max, int reduction_sum, double w, double* out, int32_t* arg, cudaStream_t st);
 // tensor-core candidate generator + exact re-rank (knn_tc_kernels.cu)
 struct TcPlan;
 bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan);
@@ -84,6 +86,7 @@ int knn_tc_splits(int64_t Q, int64_t n_ctiles);
 int knn_tc_keep(int k, int n_lists);    // candidates a list keeps at least
 int knn_tc_slots(int k, int n_lists);   // output slots per row and list
 int knn_tc_max_k();
+int knn_tc_parts();                    // candidate lists per query row and corpus split
 size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, int splits);
 cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
                           int k, int kc, const TcPlan& plan, int splits, void* workspace, int32_t* out_idx, double* out_dist,

@@ -69,6 +69,64 @@ __global__ void __launch_bounds__(256) batch_cost_kernel(const double* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// one relaxation step of the goal lower bound (P/planners/prm/prm_graph.py:143-220 runs it node by node):
+//   out[i] = min_j ( cost(a_i, b_j) + lb_b[j] ),   arg[i] = the minimising j (smallest j on ties)
+// a = the exit configurations of one mode, b = those of the modes it leads into with their bounds.  Warp per row of a,
+// lanes stride over b, the cost arithmetic is that of batch_cost_kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) minplus_cost_kernel(const double* __restrict__ a, int64_t T1, const double* __restrict__ b,
+                                                           const double* __restrict__ lb_b, int64_t T2, int D,
+                                                           const __grid_constant__ Slices sl, int per_robot_max, int reduction_sum,
+                                                           double w, double* __restrict__ out, int32_t* __restrict__ arg) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < T1; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const double* pa = a + i * D;
+        double best = __longlong_as_double(0x7ff0000000000000LL);
+        int bj = 0x7fffffff;
+        for (int64_t j = lane; j < T2; j += 32) {
+            const double* pb = b + j * D;
+            double mx = 0.0, sum = 0.0;
+            for (int r = 0; r < sl.R; r++) {
+                double d = 0.0;
+                if (per_robot_max) {
+                    for (int k = sl.start[r]; k < sl.end[r]; k++) d = fmax(d, fabs(__dsub_rn(pa[k], pb[k])));
+                } else {
+                    double s2 = 0.0;
+                    for (int k = sl.start[r]; k < sl.end[r]; k++) {
+                        const double x = __dsub_rn(pa[k], pb[k]);
+                        s2 = __dadd_rn(s2, __dmul_rn(x, x));
+                    }
+                    d = __dsqrt_rn(s2);
+                }
+                mx = r == 0 ? d : fmax(mx, d);
+                sum = r == 0 ? d : __dadd_rn(sum, d);
+            }
+            const double c = __dadd_rn(reduction_sum ? sum : __dadd_rn(mx, __dmul_rn(w, sum)), lb_b[j]);
+            if (c < best) { best = c; bj = (int)j; }     // (j ascending within a lane: ties keep the smaller j)
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+        }
+        if (lane == 0) {
+            out[i] = best;
+            if (arg) arg[i] = bj == 0x7fffffff ? -1 : bj;
+        }
+    }
+}
+
+cudaError_t launch_minplus_cost(const double* a, int64_t T1, const double* b, const double* lb_b, int64_t T2, int D, const Slices& sl,
+                                int per_robot_max, int reduction_sum, double w, double* out, int32_t* arg, cudaStream_t st) {
+    if (T1 <= 0) return cudaSuccess;
+    int64_t blocks = (T1 * 32 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    minplus_cost_kernel<<<(int)blocks, 256, 0, st>>>(a, T1, b, lb_b, T2, D, sl, per_robot_max, reduction_sum, w, out, arg);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_batch_cost(const double* a, int64_t a_stride, const double* b, int64_t N, int D, const Slices& sl, int per_robot_max,
                               int reduction_sum, double w, double* out, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;

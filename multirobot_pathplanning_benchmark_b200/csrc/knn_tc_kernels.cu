@@ -40,8 +40,12 @@ namespace mrb {
 
 constexpr int TC_TM = 128;        // query rows per CTA (UMMA M)
 constexpr int TC_STAGES = 4;      // shared-memory stages of corpus tiles, at most (TcPlan::stages)
-constexpr int TC_THREADS = 384;   // warps 0-3: producer / MMA / TMEM allocator / spare, warps 4-11: epilogue
-constexpr int TC_LIST = 80;       // candidate list entries per epilogue thread (row x column half)
+#ifndef MRB_TC_PARTS
+#define MRB_TC_PARTS 3
+#endif
+constexpr int TC_PARTS = MRB_TC_PARTS;              // epilogue warps per TMEM lane quarter: each takes every TC_PARTS-th 16-column chunk
+constexpr int TC_THREADS = 32 * (4 + 4 * TC_PARTS); // warps 0-3: producer / MMA / TMEM allocator / spare, then the epilogue warps
+constexpr int TC_LIST = TC_PARTS == 2 ? 80 : 64;    // candidate list entries per epilogue thread (row x column part)
 constexpr int TC_TRIG = TC_LIST - 16;   // a 16-column chunk can add 16 entries: compact above this fill
 constexpr int TC_SLACK = 8;       // a compaction keeps between m and m + TC_SLACK entries
 constexpr float TC_BIG = 1.0e30f;
@@ -76,6 +80,26 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// mbarrier wait with a suspend-time hint (ns): the producer and the MMA thread have stages of slack, and a hot try_wait
+// loop competes for issue slots with the epilogue warps on the same scheduler
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_H:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra WAIT_DONE_H;\n"
+        "bra WAIT_LOOP_H;\n"
+        "WAIT_DONE_H:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(ns)
+        : "memory");
+}
+#ifdef MRB_TC_SLEEP
+#define MRB_TC_WAIT(bar, parity) mbar_wait_hint(bar, parity, MRB_TC_SLEEP)
+#else
+#define MRB_TC_WAIT(bar, parity) mbar_wait(bar, parity)
+#endif
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -256,6 +280,7 @@ __device__ __forceinline__ void tc_compact(float* keys, int* idx, int n, int m, 
     *thr_out = ord2f(T);
 }
 
+template <bool RMODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const TcPlan& plan = p.plan;
@@ -263,9 +288,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
     const uint32_t b_bytes = (uint32_t)KS * tn * 32;
     unsigned char* sB = smem_raw;
     constexpr int LSTR = TC_LIST + 1;   // odd stride: the 32 lanes of a warp append to 32 different banks
-    float* lk = reinterpret_cast<float*>(sB + (size_t)n_stages * b_bytes);       // [2 * 128][LSTR] candidate keys
-    int* li = reinterpret_cast<int*>(lk + (size_t)2 * TC_TM * LSTR);              // [2 * 128][LSTR] candidate indices
-    uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)2 * TC_TM * LSTR);  // (2 * 128 * LSTR ints: a multiple of 8 bytes)
+    float* lk = reinterpret_cast<float*>(sB + (size_t)n_stages * b_bytes);              // [PARTS * 128][LSTR] candidate keys
+    int* li = reinterpret_cast<int*>(lk + (size_t)TC_PARTS * TC_TM * LSTR);              // [PARTS * 128][LSTR] candidate indices
+    uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)TC_PARTS * TC_TM * LSTR);  // (PARTS * 128 * LSTR ints: a multiple of 8 bytes)
     uint64_t* full_b = bars;                    // [STAGES] corpus tile landed
     uint64_t* empty_b = bars + TC_STAGES;       // [STAGES] corpus tile consumed by the MMAs
     uint64_t* a_full = bars + 2 * TC_STAGES;    // query tile written to tensor memory (4 warps arrive)
@@ -288,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         mbar_init(a_full, 4);
-        for (int b = 0; b < 2; b++) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 8); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 4 * TC_PARTS); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, alloc_cols);
@@ -317,7 +342,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             int s = 0;
             uint32_t ph = 0;
             for (int64_t t = 0; t < n_tiles; ++t) {
-                mbar_wait(&empty_b[s], ph ^ 1);
+                MRB_TC_WAIT(&empty_b[s], ph ^ 1);
                 mbar_arrive_expect_tx(&full_b[s], b_bytes);
                 bulk_g2s(sB + (size_t)s * b_bytes, p.B + (size_t)(t0 + t) * KS * tn * 8, b_bytes, &full_b[s]);
                 if (++s == n_stages) { s = 0; ph ^= 1; }
@@ -334,8 +359,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             for (int64_t t = 0; t < n_tiles; ++t) {
                 const int buf = (int)(t & 1);
                 const uint32_t use = (uint32_t)(t >> 1);           // how often this buffer was used before
-                mbar_wait(&tm_empty[buf], (use & 1) ^ 1);           // first use passes immediately
-                mbar_wait(&full_b[s], ph);
+                MRB_TC_WAIT(&tm_empty[buf], (use & 1) ^ 1);         // first use passes immediately
+                MRB_TC_WAIT(&full_b[s], ph);
                 tc_fence_after();
                 const uint64_t stage_off = (uint64_t)(((uint32_t)s * b_bytes) >> 4);   // added to the 14-bit address field
                 const uint32_t d_base = tmem_base + (uint32_t)(buf * buf_cols);
@@ -351,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         }
     } else if (warp >= 4) {
         // ===== epilogue: 8 warps; thread = (query row, half); 16-column chunks alternate between the halves =====
-        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        const int quarter = warp & 3, half = (warp - 4) >> 2;   // `half` = this warp's column part, 0 .. TC_PARTS - 1
         const int r_in_tile = quarter * 32 + lane;
         const int64_t row = qtile * TC_TM + r_in_tile;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -378,7 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         float thr = 3.0e38f;                                   // append what is below; everything dropped so far was >= tau
         float tau = 3.0e38f;
         const int m = p.m;
-        const bool rmode = p.radius_mode != 0;
+        constexpr bool rmode = RMODE;
         if (rmode) {
             // every point within the radius has a coarse value below (r + pad)^2 + error bound: a fixed threshold
             thr = -3.0e38f;
@@ -408,7 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             // odd number of chunks per tile is shared evenly.  (Measured alternative: each half owning every other TILE --
             // half as many barrier hand-offs per warp, but 13.6 instead of 12.1 ms: a tile then occupies its accumulator
             // buffer twice as long and a list compaction stalls the whole tile.)
-            for (int ci = (half + (int)(t & 1)) & 1; ci < chunks_per_tile; ci += 2) {
+            for (int ci = (half + (int)(t % TC_PARTS)) % TC_PARTS; ci < chunks_per_tile; ci += TC_PARTS) {
                 const int c = ci << 4;
                 float v[16], b1[16], b2[16], b3[16];
                 const uint32_t taddr = lane_addr + (uint32_t)(buf * buf_cols + c);
@@ -514,7 +539,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             }
         }
         if (row < p.Q && !rmode) {
-            const size_t lst = ((size_t)blockIdx.y * 2 + half) * p.Q + row;
+            const size_t lst = ((size_t)blockIdx.y * TC_PARTS + half) * p.Q + row;
             float* ok = p.part_key + lst * p.kc;
             int* oi = p.part_idx + lst * p.kc;
             for (int e = 0; e < p.kc; e++) {
@@ -795,7 +820,7 @@ bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan) {
     int tn = (512 - 8 * plan->KS) / (2 * plan->n_acc) / 16 * 16;
     if (tn > 256) tn = 256;
     // shared memory: the candidate lists take 2 * 128 * (TC_LIST + 1) * 8 bytes; the corpus stages share the rest
-    const long avail = 224L * 1024 - (long)2 * TC_TM * (TC_LIST + 1) * 8 - 4096;
+    const long avail = 224L * 1024 - (long)TC_PARTS * TC_TM * (TC_LIST + 1) * 8 - 4096;
     int stages = 0;
     for (; tn >= 16; tn -= 16) {
         stages = (int)(avail / ((long)plan->KS * tn * 32));
@@ -816,10 +841,20 @@ int knn_tc_keep(int k, int n_lists) {
     return m < 1 ? 1 : m;
 }
 int knn_tc_slots(int k, int n_lists) { return knn_tc_keep(k, n_lists) + TC_SLACK; }
-int knn_tc_max_k() { return TC_TRIG - 16 - 8; }
+int knn_tc_max_k() {   // largest k whose per-list keep count (TC_PARTS lists at least) still leaves room for a chunk
+    int k = 1;
+    while (k < 128) {
+        const double pr = 1.0 / TC_PARTS;
+        const int m = (int)((k + 1) * pr + 4.0 * sqrt((k + 1) * pr * (1.0 - pr)) + 2.999);
+        if ((m > k + 9 ? k + 9 : m) > TC_TRIG - 16) break;
+        k++;
+    }
+    return k;
+}
+int knn_tc_parts() { return TC_PARTS; }
 
 size_t knn_tc_smem_bytes(const TcPlan& plan, int /*kc*/) {
-    return (size_t)plan.stages * plan.KS * plan.tn * 32 + (size_t)2 * TC_TM * (TC_LIST + 1) * 8 + 16 + 16 * 8 + (size_t)TC_MAX_KS * 16 + 1024;
+    return (size_t)plan.stages * plan.KS * plan.tn * 32 + (size_t)TC_PARTS * TC_TM * (TC_LIST + 1) * 8 + 16 + 16 * 8 + (size_t)TC_MAX_KS * 16 + 1024;
 }
 
 int knn_tc_splits(int64_t Q, int64_t n_ctiles) {
@@ -837,7 +872,7 @@ int knn_tc_splits(int64_t Q, int64_t n_ctiles) {
 
 size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, int splits) {
     const int64_t qt = (Q + TC_TM - 1) / TC_TM, ct = (N + plan.tn - 1) / plan.tn;
-    return 256 + (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)splits * 2 * Q * (kc * 8 + 4) + (size_t)Q * 4 + 16 + (size_t)TC_REDO_FAST * TC_REDO_PARTS * (kc + 8) * 12 + 1024;
+    return 256 + (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)splits * TC_PARTS * Q * (kc * 8 + 4) + (size_t)Q * 4 + 16 + (size_t)TC_REDO_FAST * TC_REDO_PARTS * (kc + 8) * 12 + 1024;
 }
 
 cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
@@ -852,11 +887,11 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     float* B = (float*)w;
     w += (size_t)ct * plan.KS * plan.tn * 32;
     float* part_key = (float*)w;
-    w += (size_t)splits * 2 * Q * kc * 4;
+    w += (size_t)splits * TC_PARTS * Q * kc * 4;
     int* part_idx = (int*)w;
-    w += (size_t)splits * 2 * Q * kc * 4;
+    w += (size_t)splits * TC_PARTS * Q * kc * 4;
     float* part_tau = (float*)w;
-    w += (size_t)splits * 2 * Q * 4;
+    w += (size_t)splits * TC_PARTS * Q * 4;
     int* redo_rows = (int*)w;
     w += ((size_t)Q * 4 + 15) / 16 * 16;
     double* redo_d = (double*)w;
@@ -880,9 +915,9 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     p.part_tau = part_tau;
     p.plan = plan;
     const size_t smem = knn_tc_smem_bytes(plan, kc);
-    e = cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(knn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    knn_tc_kernel<<<dim3((unsigned)qt, (unsigned)splits), TC_THREADS, smem, st>>>(p);
+    knn_tc_kernel<false><<<dim3((unsigned)qt, (unsigned)splits), TC_THREADS, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t rsmem = (size_t)k * 128 * 12;
@@ -890,7 +925,7 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     do {                                                                                                                          \
         e = cudaFuncSetAttribute(knn_rerank_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);                 \
         if (e != cudaSuccess) return e;                                                                                           \
-        knn_rerank_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, rsmem, st>>>(queries, corpus, Q, D, sl, metric, k, kc, 2 * splits,  \
+        knn_rerank_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, rsmem, st>>>(queries, corpus, Q, D, sl, metric, k, kc, TC_PARTS * splits,  \
                                                                                part_key, part_idx, part_tau, max_norm, redo_rows, out_idx, out_dist,  \
                                                                                certified);                                        \
     } while (0)
@@ -963,9 +998,9 @@ cudaError_t launch_radius_tc_count(const double* queries, const double* corpus, 
     p.cap = cap;
     p.plan = plan;
     const size_t smem = knn_tc_smem_bytes(plan, 0);
-    e = cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(knn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    knn_tc_kernel<<<dim3((unsigned)qt, (unsigned)splits), TC_THREADS, smem, st>>>(p);
+    knn_tc_kernel<true><<<dim3((unsigned)qt, (unsigned)splits), TC_THREADS, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 #define MRB_RFILTER(DM)                                                                                                             \

@@ -73,6 +73,38 @@ def batch_config_cost(a: torch.Tensor, b: torch.Tensor, slices, metric: str = "e
     return out
 
 
+def minplus_cost(a: torch.Tensor, b: torch.Tensor, lb_b: torch.Tensor, slices, metric: str = "euclidean", reduction: str = "max",
+                 w: float = 0.01, return_arg: bool = False):
+    """out[i] = min_j (cost(a_i, b_j) + lb_b[j]) -- one relaxation step of the goal lower bound (prm_graph.py:143-220)"""
+    lib = _lib.load()
+    a, b, lb_b = _f64(a, "a"), _f64(b, "b"), _f64(lb_b.reshape(-1), "lb_b")
+    T1, D = a.shape
+    T2 = b.shape[0]
+    if b.shape[1] != D or lb_b.numel() != T2:
+        raise ValueError("shape mismatch")
+    s, R = _slices(slices)
+    out = torch.empty(T1, dtype=torch.float64, device=a.device)
+    arg = torch.empty(T1, dtype=torch.int32, device=a.device) if return_arg else None
+    with torch.cuda.device(a.device):
+        _lib.check(lib.mrb200_minplus_cost(a.data_ptr(), T1, b.data_ptr(), lb_b.data_ptr(), T2, D, s.ctypes.data_as(_lib.c_i32p), R,
+                                           int(metric != "euclidean"), int(reduction == "sum"), float(w), out.data_ptr(),
+                                           arg.data_ptr() if arg is not None else None, _stream(a.device)), "minplus_cost")
+    return (out, arg) if return_arg else out
+
+
+def lower_bound_to_goal_layers(layers, goal_lb, slices, metric: str = "euclidean", reduction: str = "max", w: float = 0.01):
+    """Goal lower bounds of the exit (transition) configurations of a SEQUENCE of modes, as whole-layer relaxations:
+    `layers[m]` = [T_m, D] exit configurations of mode m (the last layer = the goal configurations with bounds `goal_lb`).
+    The reference's compute_lower_bound_to_goal (prm_graph.py:143-220) reaches the same numbers by a Dijkstra over single
+    nodes, one batch_config_cost call per popped node; for a sequence of modes every path visits the layers in order, so
+    lb_m[i] = min_j (cost(layer_m[i], layer_{m+1}[j]) + lb_{m+1}[j]).  -> list of [T_m] tensors"""
+    lbs = [None] * len(layers)
+    lbs[-1] = _f64(goal_lb.reshape(-1), "goal_lb")
+    for m in range(len(layers) - 2, -1, -1):
+        lbs[m] = minplus_cost(layers[m], layers[m + 1], lbs[m + 1], slices, metric, reduction, w)
+    return lbs
+
+
 def prm_k_star(N: int, D: int) -> int:
     """k* = int(e (1 + 1/D) ln N) + 1, clipped to N (prm_graph.py:440-445)."""
     return min(int(math.e * (1 + 1 / D) * math.log(N)) + 1, N) if N > 0 else 0

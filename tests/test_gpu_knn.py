@@ -267,3 +267,38 @@ def test_radius_tensor_path_at_baseline_size(knn):
     for j in np.random.default_rng(4).choice(N, 60, replace=False):
         dj = OA.batch_config_dist(corpus[j], corpus, sl, "max_euclidean")
         assert np.array_equal(idx[off[j]:off[j + 1]], OA.radius_indices(dj, r_sel))
+
+
+def test_lower_bound_to_goal_as_layer_relaxations(knn):
+    """SURVEY 8(f)4 / VERDICT r1 missing 6: compute_lower_bound_to_goal (prm_graph.py:143-220) as whole-layer min-plus
+    relaxations on the device; numbers equal a node-by-node Dijkstra with the oracle's batch_config_cost"""
+    import heapq
+    rng = np.random.default_rng(17)
+    D, sl = 12, np.array([[0, 6], [6, 12]])
+    sizes = [37, 120, 64, 5]                       # exit configurations per mode; the last layer = goal nodes
+    layers = [rng.uniform(-3, 3, (n, D)) for n in sizes]
+    for metric, red in (("euclidean", "max"), ("max", "sum")):
+        goal_lb = np.zeros(sizes[-1])
+        got = knn.lower_bound_to_goal_layers([torch.from_numpy(l).cuda() for l in layers], torch.from_numpy(goal_lb).cuda(), sl, metric, red)
+        # reference-style Dijkstra over single nodes (costs only between consecutive layers)
+        lb = [np.full(n, np.inf) for n in sizes]
+        lb[-1][:] = 0.0
+        heap = [(0.0, len(sizes) - 1, j) for j in range(sizes[-1])]
+        heapq.heapify(heap)
+        done = set()
+        while heap:
+            c, m, j = heapq.heappop(heap)
+            if (m, j) in done or m == 0:
+                continue
+            done.add((m, j))
+            edge = OA.batch_config_cost(layers[m][j][None, :] - layers[m - 1], sl, metric, red)
+            for i, e in enumerate(edge):
+                if c + e < lb[m - 1][i]:
+                    lb[m - 1][i] = c + e
+                    heapq.heappush(heap, (c + e, m - 1, i))
+        for m in range(len(sizes)):
+            assert np.allclose(got[m].cpu().numpy(), lb[m], rtol=1e-14, atol=0), (metric, red, m)
+    out, arg = knn.minplus_cost(torch.from_numpy(layers[0]).cuda(), torch.from_numpy(layers[1]).cuda(),
+                                torch.zeros(sizes[1], dtype=torch.float64, device="cuda"), sl, return_arg=True)
+    c01 = np.stack([OA.batch_config_cost(layers[0][i][None, :] - layers[1], sl, "euclidean", "max") for i in range(sizes[0])])
+    assert np.array_equal(arg.cpu().numpy(), c01.argmin(1)) and np.array_equal(out.cpu().numpy(), c01.min(1))
