@@ -40,8 +40,14 @@ namespace mrb {
 
 constexpr int TC_TM = 128;        // query rows per CTA (UMMA M)
 constexpr int TC_STAGES = 4;      // shared-memory stages of corpus tiles, at most (TcPlan::stages)
+// Measured (round 2, gpurun_out/r2g_knn_variants.log; four arms 100k x 100k / euclidean 100k x 100k / two arms 60k x 60k):
+// 2 epilogue warps per lane quarter 13.03 / 8.20 / 4.35 ms, 3 warps 12.75 / 9.03 / 4.18 ms -- a third warp hides latency but
+// every list then sees a third of the columns, keeps a looser threshold and appends more; 2 stays.
 #ifndef MRB_TC_PARTS
-#define MRB_TC_PARTS 3
+#define MRB_TC_PARTS 2
+#endif
+#ifndef MRB_TC_SLEEP
+#define MRB_TC_SLEEP 200      // suspend-time hint (ns) of the producer's and the MMA thread's mbarrier waits: -0.1 ms
 #endif
 constexpr int TC_PARTS = MRB_TC_PARTS;              // epilogue warps per TMEM lane quarter: each takes every TC_PARTS-th 16-column chunk
 constexpr int TC_THREADS = 32 * (4 + 4 * TC_PARTS); // warps 0-3: producer / MMA / TMEM allocator / spare, then the epilogue warps
@@ -95,7 +101,7 @@ __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, u
         "r"(parity), "r"(ns)
         : "memory");
 }
-#ifdef MRB_TC_SLEEP
+#if MRB_TC_SLEEP > 0
 #define MRB_TC_WAIT(bar, parity) mbar_wait_hint(bar, parity, MRB_TC_SLEEP)
 #else
 #define MRB_TC_WAIT(bar, parity) mbar_wait(bar, parity)
