@@ -46,9 +46,13 @@ constexpr int TC_STAGES = 4;      // shared-memory stages of corpus tiles, at mo
 #ifndef MRB_TC_PARTS
 #define MRB_TC_PARTS 2
 #endif
+#ifndef MRB_TC_NBUF
+#define MRB_TC_NBUF 2         // accumulator buffers in tensor memory (tile t uses buffer t % NBUF)
+#endif
 #ifndef MRB_TC_SLEEP
 #define MRB_TC_SLEEP 200      // suspend-time hint (ns) of the producer's and the MMA thread's mbarrier waits: -0.1 ms
 #endif
+constexpr int TC_NBUF = MRB_TC_NBUF;
 constexpr int TC_PARTS = MRB_TC_PARTS;              // epilogue warps per TMEM lane quarter: each takes every TC_PARTS-th 16-column chunk
 constexpr int TC_THREADS = 32 * (4 + 4 * TC_PARTS); // warps 0-3: producer / MMA / TMEM allocator / spare, then the epilogue warps
 constexpr int TC_LIST = TC_PARTS == 2 ? 80 : 64;    // candidate list entries per epilogue thread (row x column part)
@@ -300,9 +304,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
     uint64_t* full_b = bars;                    // [STAGES] corpus tile landed
     uint64_t* empty_b = bars + TC_STAGES;       // [STAGES] corpus tile consumed by the MMAs
     uint64_t* a_full = bars + 2 * TC_STAGES;    // query tile written to tensor memory (4 warps arrive)
-    uint64_t* tm_full = a_full + 1;             // [2] accumulators ready
-    uint64_t* tm_empty = tm_full + 2;           // [2] accumulators drained by the epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
+    uint64_t* tm_full = a_full + 1;             // [NBUF] accumulators ready
+    uint64_t* tm_empty = tm_full + TC_NBUF;     // [NBUF] accumulators drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + TC_NBUF);
     // issue table of the MMA thread, one entry per K step: B descriptor of stage 0, A column, accumulator column
     // offset | accumulate flag << 31 (descriptor arithmetic inside the issue loop costs the single issuing thread more
     // cycles per instruction than the tensor pipe needs to run it)
@@ -312,14 +316,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int buf_cols = n_acc * tn;            // TMEM columns per accumulator buffer
-    const uint32_t a_col0 = (uint32_t)(2 * buf_cols);   // the query operand sits behind the two accumulator buffers
+    const uint32_t a_col0 = (uint32_t)(TC_NBUF * buf_cols);   // the query operand sits behind the accumulator buffers
     uint32_t alloc_cols = 32;
     while (alloc_cols < a_col0 + (uint32_t)(8 * KS)) alloc_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         mbar_init(a_full, 4);
-        for (int b = 0; b < 2; b++) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 4 * TC_PARTS); }
+        for (int b = 0; b < TC_NBUF; b++) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 4 * TC_PARTS); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, alloc_cols);
@@ -363,8 +367,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             int s = 0;
             uint32_t ph = 0;
             for (int64_t t = 0; t < n_tiles; ++t) {
-                const int buf = (int)(t & 1);
-                const uint32_t use = (uint32_t)(t >> 1);           // how often this buffer was used before
+                const int buf = (int)(t % TC_NBUF);
+                const uint32_t use = (uint32_t)(t / TC_NBUF);      // how often this buffer was used before
                 MRB_TC_WAIT(&tm_empty[buf], (use & 1) ^ 1);         // first use passes immediately
                 MRB_TC_WAIT(&full_b[s], ph);
                 tc_fence_after();
@@ -430,8 +434,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         };
         const int chunks_per_tile = tn >> 4;   // 16-column chunks: the loads of up to four robots' accumulators fly together
         for (int64_t t = 0; t < n_tiles; ++t) {
-            const int buf = (int)(t & 1);
-            const uint32_t use = (uint32_t)(t >> 1);
+            const int buf = (int)(t % TC_NBUF);
+            const uint32_t use = (uint32_t)(t / TC_NBUF);
             mbar_wait(&tm_full[buf], use & 1);
             tc_fence_after();
             const int64_t col0 = (t0 + t) * tn;
@@ -821,9 +825,9 @@ bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan) {
         plan->KS += plan->ksteps[a];
     }
     if (plan->KS > TC_MAX_KS) return false;
-    // tensor memory: two accumulator buffers of n_acc x tn columns and the query operand (8 columns per K step) in 512
+    // tensor memory: TC_NBUF accumulator buffers of n_acc x tn columns and the query operand (8 columns per K step) in 512
     // columns; the UMMA N of a 128-row instruction is a multiple of 16
-    int tn = (512 - 8 * plan->KS) / (2 * plan->n_acc) / 16 * 16;
+    int tn = (512 - 8 * plan->KS) / (TC_NBUF * plan->n_acc) / 16 * 16;
     if (tn > 256) tn = 256;
     // shared memory: the candidate lists take 2 * 128 * (TC_LIST + 1) * 8 bytes; the corpus stages share the rest
     const long avail = 224L * 1024 - (long)TC_PARTS * TC_TM * (TC_LIST + 1) * 8 - 4096;
