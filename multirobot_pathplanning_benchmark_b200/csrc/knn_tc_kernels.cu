@@ -449,9 +449,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
                 const uint32_t taddr = lane_addr + (uint32_t)(buf * buf_cols + c);
                 // issue every accumulator's load before the one wait (n_acc is uniform across the CTA)
                 tmem_ld16(taddr, v);
+#if defined(MRB_TC_ABL) && MRB_TC_ABL == 2   // experiment build: one accumulator read instead of n_acc (timing only)
+#pragma unroll
+                for (int j = 0; j < 16; j++) { b1[j] = v[j]; b2[j] = v[j]; b3[j] = v[j]; }
+#else
                 if (n_acc > 1) tmem_ld16(taddr + (uint32_t)tn, b1);
                 if (n_acc > 2) tmem_ld16(taddr + (uint32_t)(2 * tn), b2);
                 if (n_acc > 3) tmem_ld16(taddr + (uint32_t)(3 * tn), b3);
+#endif
                 tmem_ld_wait();
                 if (n_acc == 2) {
 #pragma unroll
@@ -483,6 +488,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 4; j++) lo4[j] = fminf(lo8[j], lo8[4 + j]);
                 const float lo = fminf(fminf(lo4[0], lo4[1]), fminf(lo4[2], lo4[3]));
+#if defined(MRB_TC_ABL) && MRB_TC_ABL == 1   // experiment build: no candidate path at all (timing only)
+                if (lo < -1.0e30f) mk[0] = lo;
+                continue;
+#endif
                 if (!__any_sync(TC_FULL, lo < thr)) continue;
                 if (lo < thr) {
                     const int64_t cbase = col0 + c;
