@@ -724,19 +724,12 @@ int mrb200_minplus_cost(const double* a, int64_t T1, const double* b, const doub
     return MRB200_OK;
 }
 
-static int tc_max_splits(int64_t Q) {   // upper bound of knn_tc_splits for any corpus
-    const int64_t qt = (Q + 127) / 128;
-    int64_t s = (160 + qt - 1) / qt;
-    return (int)(s > 32 ? 32 : s < 1 ? 1 : s);
-}
-
 static size_t tc_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
     // sized for the worst plan: K steps of the euclidean plan + one per robot (<= 8 accumulators), the narrowest tile
     const int ks = (D + 2 + 7) / 8 + 8;
-    const int splits = tc_max_splits(Q);
-    const size_t lists = (size_t)splits * mrb::knn_tc_parts();
+    const size_t lists = (size_t)mrb::knn_tc_max_lists(Q);
     return 256 + align256((size_t)((Q + 127) / 128) * ks * 128 * 32) + align256((size_t)(N + 256) * ks * 32) +
-           align256(lists * (size_t)Q * ((size_t)(k + 16) * 8 + 4)) + align256((size_t)Q * 4 + 16) + align256((size_t)1024 * 32 * (size_t)k * 12) + align256((size_t)Q) + 4096;
+           align256(lists * ((size_t)(k + 16) * 8 + 4)) + align256((size_t)Q * 4 + 16) + align256((size_t)1024 * 32 * (size_t)k * 12) + align256((size_t)Q) + 4096;
 }
 
 size_t mrb200_knn_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
@@ -773,10 +766,9 @@ int mrb200_knn(const double* queries, const double* corpus, int64_t Q, int64_t N
     const uint8_t* skip = nullptr;
     if (use_tc) {
         const int64_t ct = (N + plan.tn - 1) / plan.tn;
-        const int tsplits = mrb::knn_tc_splits(Q, ct);
-        const int kc = mrb::knn_tc_slots(k, mrb::knn_tc_parts() * tsplits);   // output slots per row and list
+        const int kc = mrb::knn_tc_slots(k, mrb::knn_tc_min_lists(Q, ct));   // output slots per row and list
         uint8_t* certified = tc_ws;
-        cudaError_t e = mrb::launch_knn_tc(queries, corpus, Q, N, D, sl, metric, k, kc, plan, tsplits, tc_ws + align256((size_t)Q), out_idx,
+        cudaError_t e = mrb::launch_knn_tc(queries, corpus, Q, N, D, sl, metric, k, kc, plan, tc_ws + align256((size_t)Q), out_idx,
                                            out_dist, certified, st);
         if (e != cudaSuccess) return cuda_fail(e, "knn (tensor-core path)");
         g_launches += 6;   // 2 x operand preparation, candidate generator, re-rank, exact rows without a certificate + their merge

@@ -82,14 +82,16 @@ cudaError_t launch_minplus_cost(const double* a, int64_t T1, const double* b, co
 struct TcPlan;
 bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan);
 size_t knn_tc_smem_bytes(const TcPlan& plan, int kc);
-int knn_tc_splits(int64_t Q, int64_t n_ctiles);
+void knn_tc_shape(int64_t Q, int64_t n_ctiles, int64_t* full_qtiles, int* tail_splits);   // work decomposition of a launch
+int64_t knn_tc_max_lists(int64_t Q);                    // candidate lists a launch writes, at most
+int knn_tc_min_lists(int64_t Q, int64_t n_ctiles);      // lists per row, at least
 int knn_tc_keep(int k, int n_lists);    // candidates a list keeps at least
 int knn_tc_slots(int k, int n_lists);   // output slots per row and list
 int knn_tc_max_k();
 int knn_tc_parts();                    // candidate lists per query row and corpus split
-size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, int splits);
+size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc);
 cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
-                          int k, int kc, const TcPlan& plan, int splits, void* workspace, int32_t* out_idx, double* out_dist,
+                          int k, int kc, const TcPlan& plan, void* workspace, int32_t* out_idx, double* out_dist,
                           uint8_t* certified, cudaStream_t st);
 size_t radius_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int cap);
 cudaError_t launch_radius_tc_count(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,

@@ -32,6 +32,7 @@ struct TcPlan {
     int KS;                  // total K steps
     int tn;                  // corpus columns per accumulator tile (UMMA N)
     int stages;              // shared-memory stages of corpus tiles (2..4)
+    int sc;                  // columns an epilogue warp reads per tcgen05.ld batch (0: generic 16-column epilogue, > 4 accumulators)
 };
 
 // distance between q (registers / local) and p (any memory), fp64, reference operand order:

@@ -16,8 +16,11 @@
 // for the life of the CTA (tcgen05.st once, then every MMA reads A from TMEM: shared memory only feeds the small B tile).
 // knn_tc_kernel: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (M = 128 query rows, N = corpus columns per
 // accumulator, K = 8 per instruction, kind::tf32, FP32 accumulators in TMEM, one accumulator per robot, double
-// buffered), warp 2 = TMEM allocator, warps 4-11 = epilogue: tcgen05.ld of 16 columns per robot, max over robots, a min
-// tree + warp vote that skips chunks without a candidate, else THRESHOLD-FIRST selection: values below the thread's
+// buffered), warp 2 = TMEM allocator, warps 4-11 = epilogue: each warp owns a lane quarter and a contiguous column part of
+// every tile, reads its SC columns of every robot's accumulator with one batch of tcgen05.ld, RELEASES the accumulator
+// buffer as soon as the loads have landed (the MMAs of the tile after next overlap the selection work below; a warp that
+// is busy compacting a list no longer holds tensor memory), then: max over robots, a min tree + warp vote that skips
+// batches without a candidate, else THRESHOLD-FIRST selection: values below the thread's
 // current threshold are appended to its list in shared memory (no ordering); when a list fills up, the warp bisects
 // for the value that keeps about `m` entries, drops the rest and lowers the threshold.  knn_rerank_kernel recomputes the
 // candidates' distances in fp64 with the reference's operand order, sorts by (distance, index) and certifies each
@@ -61,6 +64,10 @@ constexpr int TC_SLACK = 8;       // a compaction keeps between m and m + TC_SLA
 constexpr float TC_BIG = 1.0e30f;
 constexpr int TC_MAX_KS = 40;     // knn_tc_make_plan accepts plans up to this many K steps
 constexpr unsigned TC_FULL = 0xffffffffu;
+constexpr int TC_MAX_SMS = 192;   // the tail decomposition never assumes more SMs than this (workspace bound)
+#ifndef MRB_TC_FAST_EPILOGUE
+#define MRB_TC_FAST_EPILOGUE 1  // 0: experiment build with the generic epilogue for every plan
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM primitives
@@ -123,6 +130,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
+}
+// 8 consecutive FP32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// SC (a multiple of 8) consecutive columns as x16 pieces and at most one x8 piece
+template <int SC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+#pragma unroll
+    for (int c = 0; c + 16 <= SC; c += 16) tmem_ld16(taddr + (uint32_t)c, v + c);
+    if constexpr (SC % 16 == 8) tmem_ld8(taddr + (uint32_t)(SC - 8), v + (SC - 8));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 8 consecutive 32-bit columns of this thread's TMEM lane <- registers
@@ -207,13 +229,17 @@ struct TcParams {
     const float* A;      // prepared queries  [Q padded to 128][8 KS], row-major
     const float* B;      // prepared corpus   [c tiles][KS][tn x 8], UMMA layout
     int64_t Q, N;
-    int64_t tiles_per_split;  // corpus tiles per split
+    // work decomposition (1-D grid): CTAs [0, full_qtiles) sweep the whole corpus for one query tile each; the remaining
+    // query tiles (the last, partial wave of the grid) are split tail_splits ways along the corpus so that they end
+    // together with ~1 / tail_splits of a full sweep.  Small query sets: full_qtiles = 0, every tile is split.
+    int64_t full_qtiles;
+    int tail_splits;
     int64_t n_ctiles;
     int m;                    // entries a compaction keeps (at least)
     int kc;                   // output slots per row and list = m + TC_SLACK
-    float* part_key;          // [split][half][Q][kc]
+    float* part_key;          // [list][kc], list = tc_list_id(row, split, part)
     int* part_idx;
-    float* part_tau;          // [split][half][Q]: every point NOT in the list has a coarse value >= tau
+    float* part_tau;          // [list]: every point of the list's corpus part NOT in the list has a coarse value >= tau
     // radius mode (r-disc search): fixed per-row thresholds, candidates appended to per-row buffers in global memory
     int radius_mode;
     const double* radii;      // [Q] or null
@@ -225,6 +251,12 @@ struct TcParams {
     int cap;
     TcPlan plan;
 };
+
+// candidate lists of a row are consecutive: TC_PARTS per corpus split; rows of the full query tiles have one split
+__host__ __device__ inline int64_t tc_list_id(int64_t row, int split, int part, int64_t full_rows, int tail_splits) {
+    if (row < full_rows) return row * TC_PARTS + part;
+    return full_rows * TC_PARTS + ((row - full_rows) * tail_splits + split) * TC_PARTS + part;
+}
 
 // Warp-cooperative compaction of lane `src`'s candidate list (n entries at keys/idx + base): bisect (over the ordered
 // bit patterns of the keys) for the smallest threshold T that keeps at least m entries, stop as soon as the kept count
@@ -290,7 +322,10 @@ __device__ __forceinline__ void tc_compact(float* keys, int* idx, int n, int m, 
     *thr_out = ord2f(T);
 }
 
-template <bool RMODE>
+// NACC / SC > 0: fast epilogue for exactly NACC accumulators, SC columns per warp and load batch (plan.sc); NACC = 0:
+// generic epilogue (any number of accumulators, 16-column chunks alternating between the parts, buffer held until the
+// tile's selection work is done)
+template <bool RMODE, int NACC, int SC>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const TcPlan& plan = p.plan;
@@ -341,9 +376,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t qtile = blockIdx.x;
-    const int64_t t0 = blockIdx.y * p.tiles_per_split;
-    const int64_t t1 = min(p.n_ctiles, t0 + p.tiles_per_split);
+    int64_t qtile = blockIdx.x;
+    int split = 0, n_split = 1;
+    if (qtile >= p.full_qtiles) {
+        const int64_t r = qtile - p.full_qtiles;
+        qtile = p.full_qtiles + r / p.tail_splits;
+        split = (int)(r % p.tail_splits);
+        n_split = p.tail_splits;
+    }
+    const int64_t tiles_per_split = (p.n_ctiles + n_split - 1) / n_split;
+    const int64_t t0 = split * tiles_per_split;
+    const int64_t t1 = min(p.n_ctiles, t0 + tiles_per_split);
     const int64_t n_tiles = max((int64_t)0, t1 - t0);
 
     if (warp == 0) {
@@ -432,111 +475,200 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
                 n = 0;
             }
         };
-        const int chunks_per_tile = tn >> 4;   // 16-column chunks: the loads of up to four robots' accumulators fly together
-        for (int64_t t = 0; t < n_tiles; ++t) {
-            const int buf = (int)(t % TC_NBUF);
-            const uint32_t use = (uint32_t)(t / TC_NBUF);
-            mbar_wait(&tm_full[buf], use & 1);
-            tc_fence_after();
-            const int64_t col0 = (t0 + t) * tn;
-            // the two halves take alternate 16-column chunks of every tile; the parity flips from tile to tile so that an
-            // odd number of chunks per tile is shared evenly.  (Measured alternative: each half owning every other TILE --
-            // half as many barrier hand-offs per warp, but 13.6 instead of 12.1 ms: a tile then occupies its accumulator
-            // buffer twice as long and a list compaction stalls the whole tile.)
-            for (int ci = (half + (int)(t % TC_PARTS)) % TC_PARTS; ci < chunks_per_tile; ci += TC_PARTS) {
-                const int c = ci << 4;
-                float v[16], b1[16], b2[16], b3[16];
-                const uint32_t taddr = lane_addr + (uint32_t)(buf * buf_cols + c);
-                // issue every accumulator's load before the one wait (n_acc is uniform across the CTA)
-                tmem_ld16(taddr, v);
-#if defined(MRB_TC_ABL) && MRB_TC_ABL == 2   // experiment build: one accumulator read instead of n_acc (timing only)
-#pragma unroll
-                for (int j = 0; j < 16; j++) { b1[j] = v[j]; b2[j] = v[j]; b3[j] = v[j]; }
-#else
-                if (n_acc > 1) tmem_ld16(taddr + (uint32_t)tn, b1);
-                if (n_acc > 2) tmem_ld16(taddr + (uint32_t)(2 * tn), b2);
-                if (n_acc > 3) tmem_ld16(taddr + (uint32_t)(3 * tn), b3);
-#endif
-                tmem_ld_wait();
-                if (n_acc == 2) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], b1[j]);
-                } else if (n_acc == 3) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] = fmaxf(fmaxf(v[j], b1[j]), b2[j]);   // three-input max
-                } else if (n_acc >= 4) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] = fmaxf(fmaxf(v[j], b1[j]), fmaxf(b2[j], b3[j]));
+        // one list at a time, the whole warp compacts the lists that could not take another 16 columns
+        auto compact_full_lists = [&]() {
+            unsigned need = __ballot_sync(TC_FULL, n > TC_TRIG);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1u;
+                const int cnt = __shfl_sync(TC_FULL, n, src);
+                __syncwarp();
+                int kept;
+                float nt;
+                tc_compact(wk + (size_t)src * LSTR, wi + (size_t)src * LSTR, cnt, m, lane, &kept, &nt);
+                if (lane == src) {
+                    if (kept < 0) { n = 0; thr = -3.0e38f; tau = -3.0e38f; }   // closed: exact fallback for this row
+                    else { n = kept; thr = nt; tau = nt; }
                 }
-                for (int a = 4; a < n_acc; a += 2) {  // more than four robots: two more at a time
-                    tmem_ld16(taddr + (uint32_t)(a * tn), b1);
-                    if (a + 1 < n_acc) tmem_ld16(taddr + (uint32_t)((a + 1) * tn), b2);
+                __syncwarp();
+            }
+        };
+        if constexpr (NACC > 0) {
+            // ===== fast epilogue: this warp owns columns [half * w, (half + 1) * w) of every tile, w = n_sub * SC =====
+            const int w = tn / TC_PARTS, n_sub = w / SC;
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const int buf = (int)(t % TC_NBUF);
+                const uint32_t use = (uint32_t)(t / TC_NBUF);
+                mbar_wait(&tm_full[buf], use & 1);
+                tc_fence_after();
+                const uint32_t tbase = lane_addr + (uint32_t)(buf * buf_cols + half * w);
+                const int64_t colw = (t0 + t) * tn + half * w;
+                for (int sub = 0; sub < n_sub; ++sub) {
+                    float va[NACC][SC];
+#pragma unroll
+                    for (int a = 0; a < NACC; a++) tmem_ld_cols<SC>(tbase + (uint32_t)(a * tn + sub * SC), va[a]);
                     tmem_ld_wait();
-                    if (a + 1 < n_acc) {
+                    if (sub == n_sub - 1) {
+                        // everything this warp needs from the buffer is in registers: hand it back to the MMA thread BEFORE
+                        // the selection work (a list compaction takes as long as several tiles)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tm_empty[buf]);
+                    }
+                    float* v = va[0];
+                    if constexpr (NACC == 2) {
 #pragma unroll
-                        for (int j = 0; j < 16; j++) v[j] = fmaxf(fmaxf(v[j], b1[j]), b2[j]);
-                    } else {
+                        for (int j = 0; j < SC; j++) v[j] = fmaxf(v[j], va[1][j]);
+                    } else if constexpr (NACC == 3) {
 #pragma unroll
-                        for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], b1[j]);
+                        for (int j = 0; j < SC; j++) v[j] = fmaxf(fmaxf(v[j], va[1][j]), va[2][j]);
+                    } else if constexpr (NACC == 4) {
+#pragma unroll
+                        for (int j = 0; j < SC; j++) v[j] = fmaxf(fmaxf(v[j], va[1][j]), fmaxf(va[2][j], va[3][j]));
+                    }
+                    // minima: per 16-column block, per group g = column mod 4 -- a lane that holds a candidate only looks
+                    // at the groups below its threshold
+                    constexpr int NB = (SC + 15) / 16;
+                    float g4[NB][4], bl[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            float x = v[16 * b + g];
+#pragma unroll
+                            for (int jj = 1; jj < 4; jj++)
+                                if (16 * b + g + 4 * jj < SC) x = fminf(x, v[16 * b + g + 4 * jj]);
+                            g4[b][g] = x;
+                        }
+                        bl[b] = fminf(fminf(g4[b][0], g4[b][1]), fminf(g4[b][2], g4[b][3]));
+                    }
+                    float lo = bl[0];
+#pragma unroll
+                    for (int b = 1; b < NB; b++) lo = fminf(lo, bl[b]);
+                    if (!__any_sync(TC_FULL, lo < thr)) continue;
+                    const int64_t cbase = colw + sub * SC;
+                    const int lim = (int)min((int64_t)SC, p.N - cbase);   // columns of this batch that exist (last tile)
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        // append-only: no ordering, no search (n <= TC_TRIG here: room for 16 more)
+                        if (bl[b] < thr) {
+#pragma unroll
+                            for (int g = 0; g < 4; g++) {
+                                if (g4[b][g] < thr) {
+#pragma unroll
+                                    for (int jj = 0; jj < 4; jj++) {
+                                        const int j = 16 * b + g + 4 * jj;
+                                        if (j < SC) {
+                                            if (v[j] < thr && j < lim) {
+                                                mk[n] = v[j];
+                                                mi[n] = (int)cbase + j;
+                                                n++;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        if (rmode) {
+                            if (n > TC_TRIG) spill();
+                        } else {
+                            compact_full_lists();
+                        }
                     }
                 }
-                // after warm-up hardly any chunk holds a candidate: one min tree + one compare per lane, and the
-                // per-column work only when some lane of the warp needs it
-                float lo8[8], lo4[4];
-#pragma unroll
-                for (int j = 0; j < 8; j++) lo8[j] = fminf(v[j], v[8 + j]);
-#pragma unroll
-                for (int j = 0; j < 4; j++) lo4[j] = fminf(lo8[j], lo8[4 + j]);
-                const float lo = fminf(fminf(lo4[0], lo4[1]), fminf(lo4[2], lo4[3]));
-#if defined(MRB_TC_ABL) && MRB_TC_ABL == 1   // experiment build: no candidate path at all (timing only)
-                if (lo < -1.0e30f) mk[0] = lo;
-                continue;
-#endif
-                if (!__any_sync(TC_FULL, lo < thr)) continue;
-                if (lo < thr) {
-                    const int64_t cbase = col0 + c;
-                    const int lim = (int)min((int64_t)16, p.N - cbase);   // columns of this chunk that exist (last tile)
-                    // append-only: no ordering, no search (n <= TC_TRIG here: room for all 16).  lo4[g] is the minimum
-                    // of columns g, g + 4, g + 8, g + 12: only groups that hold a candidate look at their members
-#pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        if (lo4[g] < thr) {
-#pragma unroll
-                            for (int jj = 0; jj < 4; jj++) {
-                                const int j = g + 4 * jj;
-                                if (v[j] < thr && j < lim) {
-                                    mk[n] = v[j];
-                                    mi[n] = (int)cbase + j;
-                                    n++;
+            }
+        } else {
+            const int chunks_per_tile = tn >> 4;   // 16-column chunks: the loads of up to four robots' accumulators fly together
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const int buf = (int)(t % TC_NBUF);
+                const uint32_t use = (uint32_t)(t / TC_NBUF);
+                mbar_wait(&tm_full[buf], use & 1);
+                tc_fence_after();
+                const int64_t col0 = (t0 + t) * tn;
+                // the two halves take alternate 16-column chunks of every tile; the parity flips from tile to tile so that an
+                // odd number of chunks per tile is shared evenly.  (Measured alternative: each half owning every other TILE --
+                // half as many barrier hand-offs per warp, but 13.6 instead of 12.1 ms: a tile then occupies its accumulator
+                // buffer twice as long and a list compaction stalls the whole tile.)
+                for (int ci = (half + (int)(t % TC_PARTS)) % TC_PARTS; ci < chunks_per_tile; ci += TC_PARTS) {
+                    const int c = ci << 4;
+                    float v[16], b1[16], b2[16], b3[16];
+                    const uint32_t taddr = lane_addr + (uint32_t)(buf * buf_cols + c);
+                    // issue every accumulator's load before the one wait (n_acc is uniform across the CTA)
+                    tmem_ld16(taddr, v);
+    #if defined(MRB_TC_ABL) && MRB_TC_ABL == 2   // experiment build: one accumulator read instead of n_acc (timing only)
+    #pragma unroll
+                    for (int j = 0; j < 16; j++) { b1[j] = v[j]; b2[j] = v[j]; b3[j] = v[j]; }
+    #else
+                    if (n_acc > 1) tmem_ld16(taddr + (uint32_t)tn, b1);
+                    if (n_acc > 2) tmem_ld16(taddr + (uint32_t)(2 * tn), b2);
+                    if (n_acc > 3) tmem_ld16(taddr + (uint32_t)(3 * tn), b3);
+    #endif
+                    tmem_ld_wait();
+                    if (n_acc == 2) {
+    #pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], b1[j]);
+                    } else if (n_acc == 3) {
+    #pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = fmaxf(fmaxf(v[j], b1[j]), b2[j]);   // three-input max
+                    } else if (n_acc >= 4) {
+    #pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = fmaxf(fmaxf(v[j], b1[j]), fmaxf(b2[j], b3[j]));
+                    }
+                    for (int a = 4; a < n_acc; a += 2) {  // more than four robots: two more at a time
+                        tmem_ld16(taddr + (uint32_t)(a * tn), b1);
+                        if (a + 1 < n_acc) tmem_ld16(taddr + (uint32_t)((a + 1) * tn), b2);
+                        tmem_ld_wait();
+                        if (a + 1 < n_acc) {
+    #pragma unroll
+                            for (int j = 0; j < 16; j++) v[j] = fmaxf(fmaxf(v[j], b1[j]), b2[j]);
+                        } else {
+    #pragma unroll
+                            for (int j = 0; j < 16; j++) v[j] = fmaxf(v[j], b1[j]);
+                        }
+                    }
+                    // after warm-up hardly any chunk holds a candidate: one min tree + one compare per lane, and the
+                    // per-column work only when some lane of the warp needs it
+                    float lo8[8], lo4[4];
+    #pragma unroll
+                    for (int j = 0; j < 8; j++) lo8[j] = fminf(v[j], v[8 + j]);
+    #pragma unroll
+                    for (int j = 0; j < 4; j++) lo4[j] = fminf(lo8[j], lo8[4 + j]);
+                    const float lo = fminf(fminf(lo4[0], lo4[1]), fminf(lo4[2], lo4[3]));
+    #if defined(MRB_TC_ABL) && MRB_TC_ABL == 1   // experiment build: no candidate path at all (timing only)
+                    if (lo < -1.0e30f) mk[0] = lo;
+                    continue;
+    #endif
+                    if (!__any_sync(TC_FULL, lo < thr)) continue;
+                    if (lo < thr) {
+                        const int64_t cbase = col0 + c;
+                        const int lim = (int)min((int64_t)16, p.N - cbase);   // columns of this chunk that exist (last tile)
+                        // append-only: no ordering, no search (n <= TC_TRIG here: room for all 16).  lo4[g] is the minimum
+                        // of columns g, g + 4, g + 8, g + 12: only groups that hold a candidate look at their members
+    #pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            if (lo4[g] < thr) {
+    #pragma unroll
+                                for (int jj = 0; jj < 4; jj++) {
+                                    const int j = g + 4 * jj;
+                                    if (v[j] < thr && j < lim) {
+                                        mk[n] = v[j];
+                                        mi[n] = (int)cbase + j;
+                                        n++;
+                                    }
                                 }
                             }
                         }
                     }
-                }
-                if (rmode) {
-                    if (n > TC_TRIG) spill();
-                    continue;
-                }
-                // lists that could not take another chunk are compacted, one list at a time, by the whole warp
-                unsigned need = __ballot_sync(TC_FULL, n > TC_TRIG);
-                while (need) {
-                    const int src = __ffs(need) - 1;
-                    need &= need - 1u;
-                    const int cnt = __shfl_sync(TC_FULL, n, src);
-                    __syncwarp();
-                    int kept;
-                    float nt;
-                    tc_compact(wk + (size_t)src * LSTR, wi + (size_t)src * LSTR, cnt, m, lane, &kept, &nt);
-                    if (lane == src) {
-                        if (kept < 0) { n = 0; thr = -3.0e38f; tau = -3.0e38f; }   // closed: exact fallback for this row
-                        else { n = kept; thr = nt; tau = nt; }
+                    if (rmode) {
+                        if (n > TC_TRIG) spill();
+                        continue;
                     }
-                    __syncwarp();
+                    compact_full_lists();
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tm_empty[buf]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tm_empty[buf]);
         }
         if (rmode) spill();
         // final compaction to the output size (every list longer than kc), then write-out
@@ -558,7 +690,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             }
         }
         if (row < p.Q && !rmode) {
-            const size_t lst = ((size_t)blockIdx.y * TC_PARTS + half) * p.Q + row;
+            const size_t lst = (size_t)tc_list_id(row, split, half, p.full_qtiles * TC_TM, p.tail_splits);
             float* ok = p.part_key + lst * p.kc;
             int* oi = p.part_idx + lst * p.kc;
             for (int e = 0; e < p.kc; e++) {
@@ -579,7 +711,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
 template <int DMAX>
 __global__ void __launch_bounds__(128) knn_rerank_kernel(const double* __restrict__ queries, const double* __restrict__ corpus, int64_t Q,
                                                          int D, const __grid_constant__ Slices sl, int metric, int k, int kc,
-                                                         int splits, const float* __restrict__ part_key, const int* __restrict__ part_idx,
+                                                         int64_t full_rows, int tail_splits, const float* __restrict__ part_key,
+                                                         const int* __restrict__ part_idx,
                                                          const float* __restrict__ part_tau,
                                                          unsigned* __restrict__ max_norm_bits, int* __restrict__ redo_rows,
                                                          int32_t* __restrict__ out_idx,
@@ -594,15 +727,17 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const double* __restric
     for (int d = 0; d < DMAX; d++) q[d] = d < D ? queries[row * D + d] : 0.0;
     ThreadHeap<double> heap(hk + threadIdx.x, hi + threadIdx.x, 128, k, 0);
     float tau = 3.0e38f;  // smallest coarse value any discarded point can have
-    for (int s = 0; s < splits; s++) {
-        const int* pi = part_idx + ((size_t)s * Q + row) * kc;
+    const size_t lst0 = (size_t)tc_list_id(row, 0, 0, full_rows, tail_splits);
+    const int n_lists = TC_PARTS * (row < full_rows ? 1 : tail_splits);
+    for (int s = 0; s < n_lists; s++) {
+        const int* pi = part_idx + (lst0 + s) * kc;
         for (int e = 0; e < kc; e++) {
             const int idx = pi[e];
             if (idx < 0) continue;
             const double d = metric_dist<DMAX>(q, corpus + (size_t)idx * D, D, sl, metric);
             if (heap.accepts(d, idx)) heap.push(d, idx);
         }
-        tau = fminf(tau, part_tau[(size_t)s * Q + row]);   // every point outside list s has a coarse value >= its tau
+        tau = fminf(tau, part_tau[lst0 + s]);   // every point of list s's corpus part outside the list has a coarse value >= its tau
     }
     // error bound of a coarse value (single TF32 rounding of every operand entry, exact products, FP32 accumulation):
     // (2^-9 + 2^-10) * M for the cross and norm terms, M = largest squared slice norm of any query / corpus row
@@ -836,10 +971,27 @@ bool knn_tc_make_plan(int D, const Slices& sl, int metric, TcPlan* plan) {
     if (plan->KS > TC_MAX_KS) return false;
     // tensor memory: TC_NBUF accumulator buffers of n_acc x tn columns and the query operand (8 columns per K step) in 512
     // columns; the UMMA N of a 128-row instruction is a multiple of 16
-    int tn = (512 - 8 * plan->KS) / (TC_NBUF * plan->n_acc) / 16 * 16;
-    if (tn > 256) tn = 256;
-    // shared memory: the candidate lists take 2 * 128 * (TC_LIST + 1) * 8 bytes; the corpus stages share the rest
+    const int tn_max = (512 - 8 * plan->KS) / (TC_NBUF * plan->n_acc) / 16 * 16;
+    // shared memory: the candidate lists take TC_PARTS * 128 * (TC_LIST + 1) * 8 bytes; the corpus stages share the rest
     const long avail = 224L * 1024 - (long)TC_PARTS * TC_TM * (TC_LIST + 1) * 8 - 4096;
+    // fast epilogue (<= 4 accumulators): every warp reads sc columns of each accumulator at once (n_acc * sc <= 96 registers);
+    // tn = a multiple of TC_PARTS * sc
+    static const int sc_of[5] = {0, 48, 48, 32, 24};
+    plan->sc = 0;
+    if (plan->n_acc <= 4 && MRB_TC_FAST_EPILOGUE) {
+        const int sc = sc_of[plan->n_acc], unit = TC_PARTS * sc;
+        int tn = tn_max / unit * unit;
+        if (tn > 256) tn = 256 / unit * unit;
+        while (tn >= unit && (tn % 16 != 0 || avail / ((long)plan->KS * tn * 32) < 2)) tn -= unit;
+        if (tn >= unit) {
+            const int stages = (int)(avail / ((long)plan->KS * tn * 32));
+            plan->tn = tn;
+            plan->sc = sc;
+            plan->stages = stages > TC_STAGES ? TC_STAGES : stages;
+            return true;
+        }
+    }
+    int tn = tn_max > 256 ? 256 : tn_max;
     int stages = 0;
     for (; tn >= 16; tn -= 16) {
         stages = (int)(avail / ((long)plan->KS * tn * 32));
@@ -876,26 +1028,63 @@ size_t knn_tc_smem_bytes(const TcPlan& plan, int /*kc*/) {
     return (size_t)plan.stages * plan.KS * plan.tn * 32 + (size_t)TC_PARTS * TC_TM * (TC_LIST + 1) * 8 + 16 + 16 * 8 + (size_t)TC_MAX_KS * 16 + 1024;
 }
 
-int knn_tc_splits(int64_t Q, int64_t n_ctiles) {
+// Work decomposition of a launch (TcParams::full_qtiles / tail_splits).  A CTA sweeps the corpus for one query tile; the
+// grid runs in waves of one CTA per SM, so the query tiles of the last, partial wave are split along the corpus into as
+// many pieces as there are SMs left over (782 query tiles on 148 SMs: 740 full sweeps + 42 tiles x 3 splits -- 5.33
+// sweep times instead of 6).  Query sets with fewer tiles than SMs are split altogether.
+void knn_tc_shape(int64_t Q, int64_t n_ctiles, int64_t* full_qtiles, int* tail_splits) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > TC_MAX_SMS) sms = TC_MAX_SMS;
     const int64_t qt = (Q + TC_TM - 1) / TC_TM;
-    int64_t s = (sms + qt - 1) / qt;                 // at least one CTA per SM
+    const int64_t rem = qt % sms;
+    int64_t s = rem ? sms / rem : 1;
     const int64_t max_s = (n_ctiles + 15) / 16;      // at least 16 corpus tiles per split
     if (s > max_s) s = max_s;
-    if (s < 1) s = 1;
     if (s > 32) s = 32;
-    return (int)s;
+    if (s < 1) s = 1;
+    *tail_splits = (int)s;
+    *full_qtiles = s > 1 ? qt - rem : qt;
+}
+// candidate lists a launch writes, at most (workspace sizing)
+int64_t knn_tc_max_lists(int64_t Q) { return (int64_t)TC_PARTS * (Q + (int64_t)TC_TM * (TC_MAX_SMS + 1)); }
+// lists per row, at least: what the per-list keep count is derived from
+int knn_tc_min_lists(int64_t Q, int64_t n_ctiles) {
+    int64_t full;
+    int s;
+    knn_tc_shape(Q, n_ctiles, &full, &s);
+    return TC_PARTS * (full > 0 ? 1 : s);
 }
 
-size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc, int splits) {
+size_t knn_tc_workspace_bytes(int64_t Q, int64_t N, const TcPlan& plan, int kc) {
     const int64_t qt = (Q + TC_TM - 1) / TC_TM, ct = (N + plan.tn - 1) / plan.tn;
-    return 256 + (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)splits * TC_PARTS * Q * (kc * 8 + 4) + (size_t)Q * 4 + 16 + (size_t)TC_REDO_FAST * TC_REDO_PARTS * (kc + 8) * 12 + 1024;
+    return 256 + (size_t)qt * plan.KS * TC_TM * 32 + (size_t)ct * plan.KS * plan.tn * 32 + (size_t)knn_tc_max_lists(Q) * (kc * 8 + 4) + (size_t)Q * 4 + 16 + (size_t)TC_REDO_FAST * TC_REDO_PARTS * (kc + 8) * 12 + 1024;
+}
+
+// the candidate generator for the plan's epilogue shape
+template <bool RMODE>
+static cudaError_t launch_tc_generator(const TcParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+#define MRB_TC_GEN(NA, SC)                                                                                                  \
+    do {                                                                                                                    \
+        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<RMODE, NA, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                                     \
+        knn_tc_kernel<RMODE, NA, SC><<<grid, TC_THREADS, smem, st>>>(p);                                                    \
+        return cudaGetLastError();                                                                                          \
+    } while (0)
+    if (p.plan.sc == 0) MRB_TC_GEN(0, 16);
+    switch (p.plan.n_acc) {
+        case 1: MRB_TC_GEN(1, 48);
+        case 2: MRB_TC_GEN(2, 48);
+        case 3: MRB_TC_GEN(3, 32);
+        case 4: MRB_TC_GEN(4, 24);
+    }
+#undef MRB_TC_GEN
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q, int64_t N, int D, const Slices& sl, int metric,
-                          int k, int kc, const TcPlan& plan, int splits, void* workspace, int32_t* out_idx, double* out_dist,
+                          int k, int kc, const TcPlan& plan, void* workspace, int32_t* out_idx, double* out_dist,
                           uint8_t* certified, cudaStream_t st) {
     const int64_t qt = (Q + TC_TM - 1) / TC_TM, ct = (N + plan.tn - 1) / plan.tn;
     unsigned char* w = (unsigned char*)workspace;
@@ -905,12 +1094,13 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     w += (size_t)qt * plan.KS * TC_TM * 32;
     float* B = (float*)w;
     w += (size_t)ct * plan.KS * plan.tn * 32;
+    const size_t max_lists = (size_t)knn_tc_max_lists(Q);
     float* part_key = (float*)w;
-    w += (size_t)splits * TC_PARTS * Q * kc * 4;
+    w += max_lists * kc * 4;
     int* part_idx = (int*)w;
-    w += (size_t)splits * TC_PARTS * Q * kc * 4;
+    w += max_lists * kc * 4;
     float* part_tau = (float*)w;
-    w += (size_t)splits * TC_PARTS * Q * 4;
+    w += max_lists * 4;
     int* redo_rows = (int*)w;
     w += ((size_t)Q * 4 + 15) / 16 * 16;
     double* redo_d = (double*)w;
@@ -926,25 +1116,22 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     p.Q = Q;
     p.N = N;
     p.n_ctiles = ct;
-    p.tiles_per_split = (ct + splits - 1) / splits;
+    knn_tc_shape(Q, ct, &p.full_qtiles, &p.tail_splits);
     p.m = kc - TC_SLACK;
     p.kc = kc;
     p.part_key = part_key;
     p.part_idx = part_idx;
     p.part_tau = part_tau;
     p.plan = plan;
-    const size_t smem = knn_tc_smem_bytes(plan, kc);
-    e = cudaFuncSetAttribute(knn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    knn_tc_kernel<false><<<dim3((unsigned)qt, (unsigned)splits), TC_THREADS, smem, st>>>(p);
-    e = cudaGetLastError();
+    const unsigned grid = (unsigned)(p.full_qtiles + (qt - p.full_qtiles) * p.tail_splits);
+    e = launch_tc_generator<false>(p, grid, knn_tc_smem_bytes(plan, kc), st);
     if (e != cudaSuccess) return e;
     const size_t rsmem = (size_t)k * 128 * 12;
 #define MRB_RERANK(DM)                                                                                                            \
     do {                                                                                                                          \
         e = cudaFuncSetAttribute(knn_rerank_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);                 \
         if (e != cudaSuccess) return e;                                                                                           \
-        knn_rerank_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, rsmem, st>>>(queries, corpus, Q, D, sl, metric, k, kc, TC_PARTS * splits,  \
+        knn_rerank_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, rsmem, st>>>(queries, corpus, Q, D, sl, metric, k, kc, p.full_qtiles * TC_TM, p.tail_splits,  \
                                                                                part_key, part_idx, part_tau, max_norm, redo_rows, out_idx, out_dist,  \
                                                                                certified);                                        \
     } while (0)
@@ -997,14 +1184,13 @@ cudaError_t launch_radius_tc_count(const double* queries, const double* corpus, 
     if (e != cudaSuccess) return e;
     knn_tc_prep_kernel<<<(unsigned)((qt * TC_TM + 127) / 128), 128, 0, st>>>(queries, Q, qt * TC_TM, D, plan, 0, TC_TM, A, max_norm);
     knn_tc_prep_kernel<<<(unsigned)((ct * plan.tn + 127) / 128), 128, 0, st>>>(corpus, N, ct * plan.tn, D, plan, 1, plan.tn, B, max_norm);
-    const int splits = knn_tc_splits(Q, ct);
     TcParams p{};
     p.A = A;
     p.B = B;
     p.Q = Q;
     p.N = N;
     p.n_ctiles = ct;
-    p.tiles_per_split = (ct + splits - 1) / splits;
+    knn_tc_shape(Q, ct, &p.full_qtiles, &p.tail_splits);
     p.m = 1;
     p.kc = 1;
     p.radius_mode = 1;
@@ -1016,11 +1202,8 @@ cudaError_t launch_radius_tc_count(const double* queries, const double* corpus, 
     p.cand_cnt = cand_cnt;
     p.cap = cap;
     p.plan = plan;
-    const size_t smem = knn_tc_smem_bytes(plan, 0);
-    e = cudaFuncSetAttribute(knn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    knn_tc_kernel<true><<<dim3((unsigned)qt, (unsigned)splits), TC_THREADS, smem, st>>>(p);
-    e = cudaGetLastError();
+    const unsigned grid = (unsigned)(p.full_qtiles + (qt - p.full_qtiles) * p.tail_splits);
+    e = launch_tc_generator<true>(p, grid, knn_tc_smem_bytes(plan, 0), st);
     if (e != cudaSuccess) return e;
 #define MRB_RFILTER(DM)                                                                                                             \
     radius_tc_filter_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, 0, st>>>(queries, corpus, Q, D, sl, metric, radii, radius, inclusive, \
