@@ -34,6 +34,7 @@
 // (12.1 -> 14.5 ms at 100k x 100k, four arms).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "async_copy.cuh"
 #include "kernels.h"
@@ -56,12 +57,18 @@ constexpr int TC_STAGES = 4;      // shared-memory stages of corpus tiles, at mo
 #define MRB_TC_SLEEP 200      // suspend-time hint (ns) of the producer's and the MMA thread's mbarrier waits: -0.1 ms
 #endif
 constexpr int TC_NBUF = MRB_TC_NBUF;
+constexpr int TC_MMA_WARPS = 2;   // warps 1 and 3 issue alternate tiles
 constexpr int TC_PARTS = MRB_TC_PARTS;              // epilogue warps per TMEM lane quarter: each takes every TC_PARTS-th 16-column chunk
 constexpr int TC_THREADS = 32 * (4 + 4 * TC_PARTS); // warps 0-3: producer / MMA / TMEM allocator / spare, then the epilogue warps
 constexpr int TC_LIST = TC_PARTS == 2 ? 80 : 64;    // candidate list entries per epilogue thread (row x column part)
 constexpr int TC_TRIG = TC_LIST - 16;   // a 16-column chunk can add 16 entries: compact above this fill
-constexpr int TC_SLACK = 8;       // a compaction keeps between m and m + TC_SLACK entries
-constexpr float TC_BIG = 1.0e30f;
+constexpr int TC_SLACK = 8;       // the final compaction of a list keeps between m and m + TC_SLACK entries (the output slots)
+#ifndef MRB_TC_SLACK_RUN
+#define MRB_TC_SLACK_RUN 12
+#endif
+constexpr int TC_SLACK_RUN = MRB_TC_SLACK_RUN;   // compactions during the sweep accept up to m + TC_SLACK_RUN: more one-round searches
+constexpr float TC_BIG = 1.0e30f;      // squared norm of the padded corpus rows
+constexpr float TC_THR_MAX = 1.0e29f;  // no append threshold exceeds this: padded columns are never candidates
 constexpr int TC_MAX_KS = 40;     // knn_tc_make_plan accepts plans up to this many K steps
 constexpr unsigned TC_FULL = 0xffffffffu;
 constexpr int TC_MAX_SMS = 192;   // the tail decomposition never assumes more SMs than this (workspace bound)
@@ -90,8 +97,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n"
         "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-        : "memory");
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u));
+}
+// one lane of a converged warp (ptxas predicates a tensor instruction on this without a loop over the active lanes)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 // arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -250,7 +268,18 @@ struct TcParams {
     int* cand_cnt;            // [Q] candidates found (may exceed cap: the row has overflowed)
     int cap;
     TcPlan plan;
+    long long* trace;         // experiment builds (MRB_TC_TRACE): clock64 stamps of one CTA's pipeline events
 };
+#ifdef MRB_TC_TRACE
+constexpr int TC_TRACE_T0 = 1000, TC_TRACE_N = 48, TC_TRACE_EV = 20;
+#define MRB_TRACE(ev, t)                                                                                           \
+    do {                                                                                                           \
+        if (p.trace && blockIdx.x == 200 && (t) >= TC_TRACE_T0 && (t) < TC_TRACE_T0 + TC_TRACE_N)                  \
+            p.trace[(ev) * TC_TRACE_N + ((t) - TC_TRACE_T0)] = clock64();                                          \
+    } while (0)
+#else
+#define MRB_TRACE(ev, t)
+#endif
 
 // candidate lists of a row are consecutive: TC_PARTS per corpus split; rows of the full query tiles have one split
 __host__ __device__ inline int64_t tc_list_id(int64_t row, int split, int part, int64_t full_rows, int tail_splits) {
@@ -258,68 +287,103 @@ __host__ __device__ inline int64_t tc_list_id(int64_t row, int split, int part, 
     return full_rows * TC_PARTS + ((row - full_rows) * tail_splits + split) * TC_PARTS + part;
 }
 
-// Warp-cooperative compaction of lane `src`'s candidate list (n entries at keys/idx + base): bisect (over the ordered
-// bit patterns of the keys) for the smallest threshold T that keeps at least m entries, stop as soon as the kept count
-// is within [m, m + TC_SLACK]; entries with key < T move to the front.  Returns (kept count, T) to every lane.  If ties
-// make it impossible to get under TC_TRIG entries, reports keep = -1: the caller closes the list (the row is then
-// recomputed by the exact kernel).
-__device__ __forceinline__ void tc_compact(float* keys, int* idx, int n, int m, int lane, int* kept_out, float* thr_out) {
+// Warp-cooperative compaction of a candidate list (n entries, all below `bound` = the list's append threshold): find a
+// threshold T that keeps between m and m + slack entries, move the entries below T to the front, return (kept count,
+// T) to every lane.  The search probes SEVEN pivots per round (an eight-way split of the value range, counted with
+// ballots) -- one round isolates the cut among ~70 entries about every other time, a second round splits the one bucket
+// that was too full.  (Fifteen pivots with packed per-lane counts and one warp reduction per word always finish in one
+// round but the round takes as long as two of these: 9.8 against 9.6 ms.)  (Round 2 first bisected
+// the ordered bit patterns one pivot at a time: 230 cycles per probe, 2-13 probes, 1000-3000 cycles per compaction, and
+// every compaction stalls the CTA's two-buffer pipeline -- clock64 trace.)  If ties make it impossible to get under
+// `trig` entries, reports keep = -1: the caller closes the list (the row is then recomputed by the exact kernel).
+__device__ __forceinline__ void tc_compact(float* keys, int* idx, int n, int m, int slack, int trig, float bound, int lane, int* kept_out,
+                                           float* thr_out, long long* dbg = nullptr) {
     constexpr int PER = (TC_LIST + 31) / 32;
+    constexpr int NP = 7;   // pivots per round: an eight-way split of [lo, hi)
+    const long long c0 = dbg ? clock64() : 0;
     float k[PER];
-    uint32_t u[PER];
-    int id[PER];
-    uint32_t lo = 0xffffffffu, hi = 0u;
+    uint32_t lo_u = 0xffffffffu, hi_u = 0u;
 #pragma unroll
     for (int j = 0; j < PER; j++) {
         const int e = lane + 32 * j;
-        const bool have = e < n;
-        k[j] = have ? keys[e] : 0.f;
-        id[j] = have ? idx[e] : -1;
-        u[j] = have ? f2ord(k[j]) : 0xffffffffu;
-        if (have) { lo = min(lo, u[j]); hi = max(hi, u[j]); }
+        k[j] = e < n ? keys[e] : 3.0e38f;     // absent entries are never below a pivot
+        if (e < n) { lo_u = min(lo_u, f2ord(k[j])); hi_u = max(hi_u, f2ord(k[j])); }
     }
-    lo = __reduce_min_sync(TC_FULL, lo);
-    hi = __reduce_max_sync(TC_FULL, hi);
-    // invariant: count(u < lo) < m <= count(u < hi_x), hi_x = hi + 1 (everything)
-    uint64_t L = lo, H = (uint64_t)hi + 1;
-    uint32_t T = (uint32_t)min(H, (uint64_t)0xffffffffu);
-    int cnt = n;
-    while (H - L > 1) {
-        const uint64_t mid = L + ((H - L) >> 1);
-        int c = 0;
+    // invariant: count(k < lo) < m <= count(k < hi)
+    float lo = ord2f(__reduce_min_sync(TC_FULL, lo_u));
+    float hi = bound;
+    if (bound >= TC_THR_MAX) hi = ord2f(__reduce_max_sync(TC_FULL, hi_u) + 1u);   // first compaction of a list: no threshold yet
+    const long long c1 = dbg ? clock64() : 0;
+    int iters = 0, cnt = n;
+    float T = hi;
+    while (true) {
+        iters++;
+        const float w = (hi - lo) * (1.f / (NP + 1));
+        float pv[NP];
+        int c[NP];
 #pragma unroll
-        for (int j = 0; j < PER; j++) c += (uint64_t)u[j] < mid ? 1 : 0;   // (absent entries are 0xffffffff: never below mid <= hi)
-        c = __reduce_add_sync(TC_FULL, c);
-        if (c >= m) {
-            H = mid;
-            T = (uint32_t)mid;
-            cnt = c;
-            if (c <= m + TC_SLACK) break;
-        } else {
-            L = mid;
+        for (int i = 0; i < NP; i++) {
+            pv[i] = lo + w * (float)(i + 1);
+            c[i] = 0;
         }
+#pragma unroll
+        for (int j = 0; j < PER; j++)
+#pragma unroll
+            for (int i = 0; i < NP; i++) c[i] += __popc(__ballot_sync(TC_FULL, k[j] < pv[i]));
+        // the first pivot that keeps at least m entries (else the upper end itself); the last one that keeps fewer
+        float nlo = lo, nT = hi;
+        int ncnt = cnt;
+#pragma unroll
+        for (int i = NP - 1; i >= 0; i--) {
+            if (c[i] >= m) { nT = pv[i]; ncnt = c[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            if (c[i] < m) nlo = pv[i];
+        }
+        const bool stuck = nlo == lo && nT == hi;   // the pivots no longer separate anything: ties
+        T = nT;
+        cnt = ncnt;
+        if (cnt <= m + slack || stuck) break;
+        lo = nlo;
+        hi = nT;
     }
-    if (cnt > m + TC_SLACK && cnt > TC_TRIG) {   // more ties than the list can ever shed
+    const long long c2 = dbg ? clock64() : 0;
+    if (cnt > m + slack && cnt > trig) {   // more ties than the list can ever shed
         *kept_out = -1;
         *thr_out = -3.0e38f;
         return;
     }
-    __syncwarp();
+    bool keep[PER];
+    unsigned bal[PER];
+    int id[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        keep[j] = k[j] < T;
+        bal[j] = __ballot_sync(TC_FULL, keep[j]);
+        id[j] = keep[j] ? idx[lane + 32 * j] : 0;
+    }
+    __syncwarp();   // every slot has been read before any is overwritten
     int pos = 0;
 #pragma unroll
     for (int j = 0; j < PER; j++) {
-        const bool keep = u[j] < T && (lane + 32 * j) < n;
-        const unsigned bal = __ballot_sync(TC_FULL, keep);
-        if (keep) {
-            const int o = pos + __popc(bal & ((1u << lane) - 1u));
+        if (keep[j]) {
+            const int o = pos + __popc(bal[j] & ((1u << lane) - 1u));
             keys[o] = k[j];
             idx[o] = id[j];
         }
-        pos += __popc(bal);
-        __syncwarp();   // slots written in round j were read (into registers) before the loop: no hazard, but keep rounds ordered
+        pos += __popc(bal[j]);
     }
+    __syncwarp();
     *kept_out = pos;
-    *thr_out = ord2f(T);
+    *thr_out = T;
+    if (dbg && lane == 0) {
+        dbg[0] = c1 - c0;
+        dbg[1] = c2 - c1;
+        dbg[2] = clock64() - c2;
+        dbg[3] = iters;
+        dbg[4] = n;
+    }
 }
 
 // NACC / SC > 0: fast epilogue for exactly NACC accumulators, SC columns per warp and load batch (plan.sc); NACC = 0:
@@ -396,36 +460,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             uint32_t ph = 0;
             for (int64_t t = 0; t < n_tiles; ++t) {
                 MRB_TC_WAIT(&empty_b[s], ph ^ 1);
+                MRB_TRACE(7, t);
                 mbar_arrive_expect_tx(&full_b[s], b_bytes);
                 bulk_g2s(sB + (size_t)s * b_bytes, p.B + (size_t)(t0 + t) * KS * tn * 8, b_bytes, &full_b[s]);
                 if (++s == n_stages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(tn);
-            mbar_wait(a_full, 0);
+    } else if (warp == 1 || warp == 3) {
+        // ===== MMA issuers: warp 1 takes the even tiles, warp 3 the odd ones (with two accumulator buffers each warp owns
+        // one); the warps stay converged, one elected lane issues.  One issuer needs ~700 cycles per four-robot tile
+        // (barrier polls, fence, uniform-register moves, four tcgen05.mma, two commits -- a serial chain on a scheduler it
+        // shares with two epilogue warps), far more than the ~100 cycles the tensor pipe works on the tile, and the
+        // epilogue warps were waiting for accumulators a third of their time (clock64 trace, MRB_TC_TRACE). =====
+        // (Measured, round 2: a loop that read its issue table from shared memory in front of every tcgen05.mma, inside an
+        // `if (lane == 0)` branch, spent ~170 cycles per instruction -- LDS -> R2UR chains serialised behind the previous
+        // MMA by the asm memory clobber, plus the ELECT / BRA.U.ANY wrapper ptxas puts around a tensor instruction in
+        // divergent code -- 714 cycles per four-robot tile against ~100 of tensor-pipe time, and the epilogue warps waited
+        // on it for a third of their time.  Plans of up to 8 K steps keep the whole table in registers.)
+        const bool leader = elect_one();
+        const uint32_t idesc = umma_idesc_tf32(tn);
+        constexpr int REG_KS = 8;
+        uint64_t rb_[REG_KS];
+        uint32_t ra_[REG_KS], rd_[REG_KS], rp_[REG_KS];
+#pragma unroll
+        for (int kg = 0; kg < REG_KS; kg++) {
+            const int kk = kg < KS ? kg : 0;
+            rb_[kg] = iss_b[kk];
+            ra_[kg] = tmem_base + iss_a[kk];
+            rd_[kg] = tmem_base + (iss_d[kk] & 0x7fffffffu);
+            rp_[kg] = iss_d[kk] >> 31;
+        }
+        mbar_wait(a_full, 0);
+        tc_fence_after();
+        for (int64_t t = (warp == 3 ? 1 : 0); t < n_tiles; t += TC_MMA_WARPS) {
+            const int buf = (int)(t % TC_NBUF);
+            const uint32_t use = (uint32_t)(t / TC_NBUF);      // how often this buffer was used before
+            const int s = (int)(t % n_stages);
+            const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
+            if (lane == 0) MRB_TRACE(0, t);
+            MRB_TC_WAIT(&tm_empty[buf], (use & 1) ^ 1);         // first use passes immediately
+            if (lane == 0) MRB_TRACE(1, t);
+            MRB_TC_WAIT(&full_b[s], ph);
+            if (lane == 0) MRB_TRACE(2, t);
             tc_fence_after();
-            int s = 0;
-            uint32_t ph = 0;
-            for (int64_t t = 0; t < n_tiles; ++t) {
-                const int buf = (int)(t % TC_NBUF);
-                const uint32_t use = (uint32_t)(t / TC_NBUF);      // how often this buffer was used before
-                MRB_TC_WAIT(&tm_empty[buf], (use & 1) ^ 1);         // first use passes immediately
-                MRB_TC_WAIT(&full_b[s], ph);
-                tc_fence_after();
-                const uint64_t stage_off = (uint64_t)(((uint32_t)s * b_bytes) >> 4);   // added to the 14-bit address field
-                const uint32_t d_base = tmem_base + (uint32_t)(buf * buf_cols);
+            const uint64_t stage_off = (uint64_t)(((uint32_t)s * b_bytes) >> 4);   // added to the 14-bit address field
+            const uint32_t d_off = (uint32_t)(buf * buf_cols);
+            if (leader) {
+                if (KS <= REG_KS) {
+#pragma unroll
+                    for (int kg = 0; kg < REG_KS; kg++)
+                        if (kg < KS) {
+                            umma_tf32_ts(rd_[kg] + d_off, ra_[kg], rb_[kg] + stage_off, idesc, rp_[kg]);
+                            MRB_TRACE(10 + kg, t);
+                        }
+                } else {
 #pragma unroll 4
-                for (int kg = 0; kg < KS; kg++) {
-                    const uint32_t d = iss_d[kg];
-                    umma_tf32_ts(d_base + (d & 0x7fffffffu), tmem_base + iss_a[kg], iss_b[kg] + stage_off, idesc, d >> 31);
+                    for (int kg = 0; kg < KS; kg++) {
+                        const uint32_t d = iss_d[kg];
+                        umma_tf32_ts(tmem_base + d_off + (d & 0x7fffffffu), tmem_base + iss_a[kg], iss_b[kg] + stage_off, idesc, d >> 31);
+                    }
                 }
                 umma_commit(&empty_b[s]);     // the stage may be refilled once these MMAs have read it
+                MRB_TRACE(14, t);
                 umma_commit(&tm_full[buf]);   // accumulators complete
-                if (++s == n_stages) { s = 0; ph ^= 1; }
+                MRB_TRACE(15, t);
             }
+            __syncwarp();
+            if (lane == 0) MRB_TRACE(3, t);
         }
     } else if (warp >= 4) {
         // ===== epilogue: 8 warps; thread = (query row, half); 16-column chunks alternate between the halves =====
@@ -453,7 +554,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         float* wk = lk + (size_t)(hslot - lane) * LSTR;        // list of lane 0 of this warp (lists of a warp are consecutive)
         int* wi = li + (size_t)(hslot - lane) * LSTR;
         int n = 0;                                             // entries in the list
-        float thr = 3.0e38f;                                   // append what is below; everything dropped so far was >= tau
+        float thr = TC_THR_MAX;                                // append what is below; everything dropped so far was >= tau
         float tau = 3.0e38f;
         const int m = p.m;
         constexpr bool rmode = RMODE;
@@ -463,9 +564,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             if (row < p.Q) {
                 const double r = (p.radii ? p.radii[row] : p.radius) + p.radius_pad;
                 const float eps = 2.95e-3f * __uint_as_float(p.max_norm_bits[0]) + 1e-4f;
-                thr = r >= 0.0 ? __double2float_ru(r * r) * (1.f + 1e-6f) + eps : -3.0e38f;
+                thr = r >= 0.0 ? fminf(__double2float_ru(r * r) * (1.f + 1e-6f) + eps, TC_THR_MAX) : -3.0e38f;
             }
         }
+        // a list is compacted (spilled, radius mode) once it could not take the appends of another step: 16 columns per
+        // chunk in the generic epilogue, a group of SC / 4 columns in the fast one
+        constexpr int trig = TC_LIST - (NACC > 0 ? SC / 4 : 16);
         // radius mode: a full list goes to the row's global buffer (both halves of a row share it through its counter)
         auto spill = [&]() {
             if (n > 0) {
@@ -477,7 +581,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
         };
         // one list at a time, the whole warp compacts the lists that could not take another 16 columns
         auto compact_full_lists = [&]() {
-            unsigned need = __ballot_sync(TC_FULL, n > TC_TRIG);
+            unsigned need = __ballot_sync(TC_FULL, n > trig);
             while (need) {
                 const int src = __ffs(need) - 1;
                 need &= need - 1u;
@@ -485,7 +589,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
                 __syncwarp();
                 int kept;
                 float nt;
-                tc_compact(wk + (size_t)src * LSTR, wi + (size_t)src * LSTR, cnt, m, lane, &kept, &nt);
+#ifdef MRB_TC_TRACE
+                tc_compact(wk + (size_t)src * LSTR, wi + (size_t)src * LSTR, cnt, m, TC_SLACK_RUN, trig, __shfl_sync(TC_FULL, thr, src), lane, &kept, &nt,
+                           (p.trace && blockIdx.x == 200 && warp == 4) ? p.trace + 18 * TC_TRACE_N : nullptr);
+                if (p.trace && blockIdx.x == 200 && warp == 4 && lane == 0) {
+                    long long* d = p.trace + 18 * TC_TRACE_N;
+                    const int slot = (int)(d[47]++ % 8);
+                    for (int q = 0; q < 5; q++) d[5 + slot * 5 + q] = d[q];
+                }
+#else
+                tc_compact(wk + (size_t)src * LSTR, wi + (size_t)src * LSTR, cnt, m, TC_SLACK_RUN, trig, __shfl_sync(TC_FULL, thr, src), lane, &kept, &nt);
+#endif
                 if (lane == src) {
                     if (kept < 0) { n = 0; thr = -3.0e38f; tau = -3.0e38f; }   // closed: exact fallback for this row
                     else { n = kept; thr = nt; tau = nt; }
@@ -499,7 +613,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
             for (int64_t t = 0; t < n_tiles; ++t) {
                 const int buf = (int)(t % TC_NBUF);
                 const uint32_t use = (uint32_t)(t / TC_NBUF);
+                if (lane == 0 && warp == 4) MRB_TRACE(9, t);
                 mbar_wait(&tm_full[buf], use & 1);
+                if (lane == 0 && warp == 4) MRB_TRACE(4, t);
                 tc_fence_after();
                 const uint32_t tbase = lane_addr + (uint32_t)(buf * buf_cols + half * w);
                 const int64_t colw = (t0 + t) * tn + half * w;
@@ -508,6 +624,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
 #pragma unroll
                     for (int a = 0; a < NACC; a++) tmem_ld_cols<SC>(tbase + (uint32_t)(a * tn + sub * SC), va[a]);
                     tmem_ld_wait();
+                    if (lane == 0 && warp == 4) MRB_TRACE(5, t);
+                    if (lane == 0 && warp == 11) MRB_TRACE(8, t);
                     if (sub == n_sub - 1) {
                         // everything this warp needs from the buffer is in registers: hand it back to the MMA thread BEFORE
                         // the selection work (a list compaction takes as long as several tiles)
@@ -526,55 +644,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int j = 0; j < SC; j++) v[j] = fmaxf(fmaxf(v[j], va[1][j]), fmaxf(va[2][j], va[3][j]));
                     }
-                    // minima: per 16-column block, per group g = column mod 4 -- a lane that holds a candidate only looks
-                    // at the groups below its threshold
-                    constexpr int NB = (SC + 15) / 16;
-                    float g4[NB][4], bl[NB];
+                    // minima per group g = column mod 4, then of the batch
+                    float g4[4];
 #pragma unroll
-                    for (int b = 0; b < NB; b++) {
+                    for (int g = 0; g < 4; g++) {
+                        float x = v[g];
 #pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            float x = v[16 * b + g];
-#pragma unroll
-                            for (int jj = 1; jj < 4; jj++)
-                                if (16 * b + g + 4 * jj < SC) x = fminf(x, v[16 * b + g + 4 * jj]);
-                            g4[b][g] = x;
-                        }
-                        bl[b] = fminf(fminf(g4[b][0], g4[b][1]), fminf(g4[b][2], g4[b][3]));
+                        for (int j = g + 4; j < SC; j += 4) x = fminf(x, v[j]);
+                        g4[g] = x;
                     }
-                    float lo = bl[0];
-#pragma unroll
-                    for (int b = 1; b < NB; b++) lo = fminf(lo, bl[b]);
+                    const float lo = fminf(fminf(g4[0], g4[1]), fminf(g4[2], g4[3]));
+#if defined(MRB_TC_ABL) && MRB_TC_ABL == 1   // experiment build: no candidate path at all (timing only)
+                    if (lo < -1.0e30f) mk[0] = lo;
+                    continue;
+#endif
+                    if (lane == 0 && warp == 4) MRB_TRACE(6, t);
                     if (!__any_sync(TC_FULL, lo < thr)) continue;
-                    const int64_t cbase = colw + sub * SC;
-                    const int lim = (int)min((int64_t)SC, p.N - cbase);   // columns of this batch that exist (last tile)
+#ifdef MRB_TC_TRACE
+                    int tr_groups = 0, tr_comp = 0, tr_lanes = __popc(__ballot_sync(TC_FULL, lo < thr));
+#endif
+                    // Some lane holds a candidate (two batches in three, mid-sweep: 768 values per vote).  Only warp-uniform
+                    // branches from here on -- a group of SC / 4 columns is visited if any lane has a candidate in it, its
+                    // appends are predicated: nested per-lane branches cost ~700 cycles per batch for one append (clock64
+                    // trace).  Append-only: no ordering, no search; n <= TC_TRIG on entry leaves room for a group (<= 16).
+                    // Columns past the end of the corpus carry TC_BIG and thresholds never exceed TC_THR_MAX < TC_BIG.
+                    const int cbase = (int)(colw + sub * SC);
 #pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        // append-only: no ordering, no search (n <= TC_TRIG here: room for 16 more)
-                        if (bl[b] < thr) {
+                    for (int g = 0; g < 4; g++) {
+                        if (__any_sync(TC_FULL, g4[g] < thr)) {
 #pragma unroll
-                            for (int g = 0; g < 4; g++) {
-                                if (g4[b][g] < thr) {
-#pragma unroll
-                                    for (int jj = 0; jj < 4; jj++) {
-                                        const int j = 16 * b + g + 4 * jj;
-                                        if (j < SC) {
-                                            if (v[j] < thr && j < lim) {
-                                                mk[n] = v[j];
-                                                mi[n] = (int)cbase + j;
-                                                n++;
-                                            }
-                                        }
-                                    }
+                            for (int j = g; j < SC; j += 4) {
+                                if (v[j] < thr) {
+                                    mk[n] = v[j];
+                                    mi[n] = cbase + j;
+                                    n++;
                                 }
                             }
-                        }
-                        if (rmode) {
-                            if (n > TC_TRIG) spill();
-                        } else {
-                            compact_full_lists();
+#ifdef MRB_TC_TRACE
+                            tr_groups++;
+                            tr_comp += __popc(__ballot_sync(TC_FULL, n > trig));
+#endif
+                            if (rmode) {
+                                if (n > trig) spill();
+                            } else {
+                                compact_full_lists();
+                            }
                         }
                     }
+#ifdef MRB_TC_TRACE
+                    if (lane == 0 && warp == 4) {
+                        MRB_TRACE(16, t);
+                        if (p.trace && blockIdx.x == 200 && t >= TC_TRACE_T0 && t < TC_TRACE_T0 + TC_TRACE_N)
+                            p.trace[17 * TC_TRACE_N + (t - TC_TRACE_T0)] = tr_lanes | (tr_groups << 8) | (tr_comp << 16);
+                    }
+#endif
                 }
             }
         } else {
@@ -660,7 +783,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
                         }
                     }
                     if (rmode) {
-                        if (n > TC_TRIG) spill();
+                        if (n > trig) spill();
                         continue;
                     }
                     compact_full_lists();
@@ -681,7 +804,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const __grid_cons
                 __syncwarp();
                 int kept;
                 float nt;
-                tc_compact(wk + (size_t)src * LSTR, wi + (size_t)src * LSTR, cnt, m, lane, &kept, &nt);
+                tc_compact(wk + (size_t)src * LSTR, wi + (size_t)src * LSTR, cnt, m, TC_SLACK, trig, __shfl_sync(TC_FULL, thr, src), lane, &kept, &nt);
                 if (lane == src) {
                     if (kept < 0 || kept > p.kc) { n = 0; tau = -3.0e38f; }
                     else { n = kept; tau = nt; }
@@ -1124,8 +1247,48 @@ cudaError_t launch_knn_tc(const double* queries, const double* corpus, int64_t Q
     p.part_tau = part_tau;
     p.plan = plan;
     const unsigned grid = (unsigned)(p.full_qtiles + (qt - p.full_qtiles) * p.tail_splits);
+#ifdef MRB_TC_TRACE
+    static long long* trace_dev = nullptr;
+    if (!trace_dev) cudaMalloc(&trace_dev, sizeof(long long) * TC_TRACE_EV * TC_TRACE_N);
+    cudaMemsetAsync(trace_dev, 0, sizeof(long long) * TC_TRACE_EV * TC_TRACE_N, st);
+    p.trace = trace_dev;
+#endif
     e = launch_tc_generator<false>(p, grid, knn_tc_smem_bytes(plan, kc), st);
     if (e != cudaSuccess) return e;
+#ifdef MRB_TC_TRACE
+    {
+        static long long h[TC_TRACE_EV * TC_TRACE_N];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long base = h[0];
+        if (base) {
+            fprintf(stderr, "TRACE tile: mma_start mma_gotempty mma_gotB mma_committed | epi_waitfull epi_gotfull epi_loaded(w4) epi_loaded(w11) | prod_gotempty\n");
+            for (int i = 0; i < TC_TRACE_N; i++)
+                fprintf(stderr, "TRACE %4d: %7lld %7lld %7lld %7lld | %7lld %7lld %7lld %7lld | %7lld\n", TC_TRACE_T0 + i, h[0 * TC_TRACE_N + i] - base,
+                        h[1 * TC_TRACE_N + i] - base, h[2 * TC_TRACE_N + i] - base, h[3 * TC_TRACE_N + i] - base, h[9 * TC_TRACE_N + i] - base,
+                        h[4 * TC_TRACE_N + i] - base, h[5 * TC_TRACE_N + i] - base, h[8 * TC_TRACE_N + i] - base, h[7 * TC_TRACE_N + i] - base);
+            fprintf(stderr, "TRACE3 tile: warp 4: gotfull->loaded, loaded->voted, voted->appended (0 = no hit), lanes, groups, compactions, tile period\n");
+            for (int i = 0; i + 1 < TC_TRACE_N; i++) {
+                const long long v = h[17 * TC_TRACE_N + i];
+                fprintf(stderr, "TRACE3 %4d: %5lld %5lld %5lld  lanes %2lld groups %lld comp %lld  period %5lld\n", TC_TRACE_T0 + i,
+                        h[5 * TC_TRACE_N + i] - h[4 * TC_TRACE_N + i], h[6 * TC_TRACE_N + i] - h[5 * TC_TRACE_N + i],
+                        h[16 * TC_TRACE_N + i] ? h[16 * TC_TRACE_N + i] - h[6 * TC_TRACE_N + i] : 0, v & 255, (v >> 8) & 255, v >> 16,
+                        h[4 * TC_TRACE_N + i + 1] - h[4 * TC_TRACE_N + i]);
+            }
+            fprintf(stderr, "TRACE4 last compactions of warp 4: load+minmax, search, move (cycles), probes, entries\n");
+            for (int i = 0; i < 8; i++) {
+                const long long* d = h + 18 * TC_TRACE_N + 5 + i * 5;
+                fprintf(stderr, "TRACE4 %lld %lld %lld probes %lld n %lld\n", d[0], d[1], d[2], d[3], d[4]);
+            }
+            fprintf(stderr, "TRACE2 tile: gotB mma0 mma1 mma2 mma3 commit0 commit1 (relative to gotB)\n");
+            for (int i = 0; i < TC_TRACE_N; i++) {
+                const long long b2 = h[2 * TC_TRACE_N + i];
+                fprintf(stderr, "TRACE2 %4d: %5lld %5lld %5lld %5lld %5lld %5lld\n", TC_TRACE_T0 + i, h[10 * TC_TRACE_N + i] - b2, h[11 * TC_TRACE_N + i] - b2,
+                        h[12 * TC_TRACE_N + i] - b2, h[13 * TC_TRACE_N + i] - b2, h[14 * TC_TRACE_N + i] - b2, h[15 * TC_TRACE_N + i] - b2);
+            }
+        }
+    }
+#endif
     const size_t rsmem = (size_t)k * 128 * 12;
 #define MRB_RERANK(DM)                                                                                                            \
     do {                                                                                                                          \
