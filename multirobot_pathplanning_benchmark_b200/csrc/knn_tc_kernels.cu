@@ -1045,6 +1045,70 @@ __global__ void __launch_bounds__(128) radius_tc_filter_kernel(const double* __r
     counts[row] = kept;
 }
 
+// The same filter with a WARP per query row (caps up to RF_CAP): lane = candidate for the fp64 predicate, survivors
+// compacted in arrival order into shared memory (ballot prefix), a warp-synchronous bitonic sort by index, write-back to
+// the front of the row's buffer.  The thread-per-row kernel above insertion-sorts in global memory with one lane of 32
+// doing anything: 5.0-5.6 ms for 100 000 rows of ~50 candidates, as long as the candidate generator itself.
+constexpr int RF_CAP = 1024, RF_WARPS = 8;
+template <int DMAX>
+__global__ void __launch_bounds__(32 * RF_WARPS) radius_tc_filter_warp_kernel(const double* __restrict__ queries, const double* __restrict__ corpus,
+                                                                              int64_t Q, int D, const __grid_constant__ Slices sl, int metric,
+                                                                              const double* __restrict__ radii, double radius, int inclusive,
+                                                                              int cap, int* __restrict__ cand_idx, int* __restrict__ cand_cnt,
+                                                                              int64_t* __restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem_rf[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* sidx = reinterpret_cast<int*>(smem_rf) + (size_t)warp * cap;
+    const int64_t row = blockIdx.x * (int64_t)RF_WARPS + warp;
+    if (row >= Q) return;
+    const int cnt = cand_cnt[row];
+    if (cnt > cap) {          // more candidates than the buffer holds: the caller answers this row with the exact kernels
+        if (lane == 0) counts[row] = -1;
+        return;
+    }
+    double q[DMAX];
+#pragma unroll
+    for (int d = 0; d < DMAX; d++) q[d] = d < D ? queries[row * D + d] : 0.0;
+    const double r = radii ? radii[row] : radius;
+    const double lim = inclusive ? r + 1e-10 : r;
+    int* buf = cand_idx + (size_t)row * cap;
+    int kept = 0;
+    for (int e0 = 0; e0 < cnt; e0 += 32) {
+        const int e = e0 + lane;
+        bool in = false;
+        int idx = 0;
+        if (e < cnt) {
+            idx = buf[e];
+            const double d = metric_dist<DMAX>(q, corpus + (size_t)idx * D, D, sl, metric);
+            in = inclusive ? d <= lim : d < lim;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (in) sidx[kept + __popc(bal & ((1u << lane) - 1u))] = idx;
+        kept += __popc(bal);
+    }
+    int n2 = 32;
+    while (n2 < kept) n2 <<= 1;
+    for (int e = kept + lane; e < n2; e += 32) sidx[e] = 0x7fffffff;
+    __syncwarp();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < (n2 >> 1); t += 32) {
+                const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));   // lower index of the compare pair
+                const int j = i | stride;
+                const bool up = (i & size) == 0;
+                const int a = sidx[i], b = sidx[j];
+                if ((a > b) == up) { sidx[i] = b; sidx[j] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    for (int e = lane; e < kept; e += 32) buf[e] = sidx[e];
+    if (lane == 0) {
+        cand_cnt[row] = kept;
+        counts[row] = kept;
+    }
+}
+
 template <int DMAX>
 __global__ void __launch_bounds__(128) radius_tc_fill_kernel(const double* __restrict__ queries, const double* __restrict__ corpus, int64_t Q,
                                                              int D, const __grid_constant__ Slices sl, int metric, int cap,
@@ -1371,12 +1435,27 @@ cudaError_t launch_radius_tc_count(const double* queries, const double* corpus, 
 #define MRB_RFILTER(DM)                                                                                                             \
     radius_tc_filter_kernel<DM><<<(unsigned)((Q + 127) / 128), 128, 0, st>>>(queries, corpus, Q, D, sl, metric, radii, radius, inclusive, \
                                                                              cap, cand_idx, cand_cnt, counts)
-    if (D <= 8) MRB_RFILTER(8);
+#define MRB_RFILTER_W(DM)                                                                                                           \
+    do {                                                                                                                            \
+        const size_t fsmem = (size_t)RF_WARPS * cap * 4;                                                                            \
+        e = cudaFuncSetAttribute(radius_tc_filter_warp_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);        \
+        if (e != cudaSuccess) return e;                                                                                             \
+        radius_tc_filter_warp_kernel<DM><<<(unsigned)((Q + RF_WARPS - 1) / RF_WARPS), 32 * RF_WARPS, fsmem, st>>>(                  \
+            queries, corpus, Q, D, sl, metric, radii, radius, inclusive, cap, cand_idx, cand_cnt, counts);                          \
+    } while (0)
+    if (cap <= RF_CAP) {
+        if (D <= 8) MRB_RFILTER_W(8);
+        else if (D <= 16) MRB_RFILTER_W(16);
+        else if (D <= 24) MRB_RFILTER_W(24);
+        else if (D <= 32) MRB_RFILTER_W(32);
+        else MRB_RFILTER_W(64);
+    } else if (D <= 8) MRB_RFILTER(8);
     else if (D <= 16) MRB_RFILTER(16);
     else if (D <= 24) MRB_RFILTER(24);
     else if (D <= 32) MRB_RFILTER(32);
     else MRB_RFILTER(64);
 #undef MRB_RFILTER
+#undef MRB_RFILTER_W
     return cudaGetLastError();
 }
 

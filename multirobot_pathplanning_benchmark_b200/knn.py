@@ -215,6 +215,7 @@ def batch_radius(queries: torch.Tensor, corpus: torch.Tensor, radius: Union[floa
                                               ws.data_ptr(), ws_bytes, counts.data_ptr(), _stream(dev)), "radius_tc_count")
         over = torch.nonzero(counts < 0).flatten()        # rows with more than `cap` candidates
         n_over = int(over.numel())
+        LAST_STATS["radius_overflow_rows"] = n_over
         if mode == "auto" and n_over > Q // 4:             # a radius this wide is not a candidate-list problem
             off, idx, dist = _radius_exact(queries, corpus, r, radii, slices, metric, inclusive, return_dist)
             return (off, idx, dist) if return_dist else (off, idx)

@@ -8,4 +8,4 @@ for v in $VARIANTS; do
   MRB200_LIB=$LIB timeout 300 python scripts/knn_check.py 100000 euclidean 2>&1 | tail -1 >> $L
   MRB200_LIB=$LIB timeout 300 python scripts/knn_check.py 60000 max_euclidean 2 2>&1 | tail -1 >> $L
 done
-cut -c1-75,130-300 $L
+cut -c1-50,78-125,190-300 $L
