@@ -41,6 +41,14 @@ extern __shared__ __align__(128) unsigned char smem_raw[];
 
 // (shared-memory pointers only: a global pointer stored next to them makes nvcc address the whole struct's
 // pointers through global stores -- STG.E to a shared-window address faults)
+// Narrowphase batches drained back to back once DRAIN_BATCH x 32 survivors are queued (experiment switch MRB_DRAIN_BATCH):
+// a second pass through the same drain routine finds its instructions in the instruction caches.
+#ifndef MRB_DRAIN_BATCH
+#define MRB_DRAIN_BATCH 1
+#endif
+constexpr int DRAIN_BATCH = MRB_DRAIN_BATCH;
+constexpr int QCAP_WORDS = 32 * (DRAIN_BATCH + 1);   // queue entries per warp
+
 struct Smem {
     uint32_t* blob;  // staged prefix of the scene blob
     float* q[2];     // configuration tiles [TILE][D]
@@ -73,7 +81,7 @@ __host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_w
     off[2] = o; o = align16(o + (edges ? 0 : size_t(TILE) * D * 4));  // second configuration buffer: configuration kernel only
     off[3] = o; o = align16(o + size_t(world_words) * TILE * 4);
     off[4] = o; o = align16(o + size_t(2) * TILE * 4);
-    off[5] = o; o = align16(o + size_t(MAX_WARPS) * 64 * 4);
+    off[5] = o; o = align16(o + size_t(MAX_WARPS) * QCAP_WORDS * 4);
     off[6] = o; o = align16(o + size_t(n_shapes));
     off[7] = o; o = align16(o + 3 * 8);
     off[8] = o; o = align16(o + (edges ? EDGE_MISC * 4 : pool ? CFG_MISC * 4 : 0));
@@ -231,7 +239,7 @@ __device__ __noinline__ void fk_call(uint32_t o_blob, uint32_t o_q, uint32_t o_W
 // phase 2: broadphase (lane = configuration, uniform over the pair list) -> per-warp queue of
 // surviving (configuration, pair) items -> exact narrowphase, 32 queued items at a time
 // ------------------------------------------------------------------------------------------
-constexpr int QCAP = 64;                  // queue entries per warp
+constexpr int QCAP = QCAP_WORDS;          // queue entries per warp
 constexpr float PEN_SCALE = 67108864.f;   // penetration accumulates in units of 2^-26 m (order independent)
 constexpr float CULL_SLACK = 1e-3f;       // bounding-volume tests keep everything closer than 1 mm
 
@@ -430,21 +438,25 @@ struct Survivors {
             }
             qn += __popc(m);
             __syncwarp();
-            if (qn >= TILE) {
-                const uint32_t entry = c.queue[c.lane];
-                const uint32_t tail = c.queue[TILE + c.lane];
+            if (qn >= DRAIN_BATCH * TILE) {
+                uint32_t entry[DRAIN_BATCH];
+#pragma unroll
+                for (int b = 0; b < DRAIN_BATCH; b++) entry[b] = c.queue[b * TILE + c.lane];
+                const uint32_t tail = c.queue[DRAIN_BATCH * TILE + c.lane];
                 __syncwarp();
-                qn -= TILE;
+                qn -= DRAIN_BATCH * TILE;
                 if (c.lane < qn) c.queue[c.lane] = tail;
                 __syncwarp();
-                drain_any(args, type, entry, true);
+#pragma unroll
+                for (int b = 0; b < DRAIN_BATCH; b++) drain_any(args, type, entry[b], true);
             }
         }
     }
     __device__ __forceinline__ void finish() {
-        if (qn > 0) {
-            const uint32_t entry = c.queue[c.lane];
-            drain_any(args, type, entry, c.lane < qn);
+#pragma unroll 1
+        for (int b = 0; b * TILE < qn; b++) {
+            const uint32_t entry = c.queue[b * TILE + c.lane];
+            drain_any(args, type, entry, b * TILE + c.lane < qn);
         }
         qn = 0;
         __syncwarp();

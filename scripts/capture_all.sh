@@ -16,4 +16,18 @@ cap edges_box_rearrangement_local check_edges_kernel 3 python scripts/prof_drive
 cap edges_box_rearrangement_uniform check_edges_kernel 3 python scripts/prof_driver.py edges box_rearrangement 16384 uniform
 cap edges_box_stacking_local check_edges_kernel 3 python scripts/prof_driver.py edges box_stacking 65536 local
 cap knn_tc knn_tc_kernel 2 python scripts/prof_driver.py knn 100000 tensor
-cap radius radius_kernel 2 python scripts/prof_driver.py radius 100000
+cap radius_tc knn_tc_kernel 2 python scripts/prof_driver.py radius 100000
+cap radius_filter radius_tc_filter_warp_kernel 1 python scripts/prof_driver.py radius 100000
+cap knn_rerank knn_rerank_kernel 2 python scripts/prof_driver.py knn 100000 tensor
+# summaries on the box (gpurun brings back at most 64 MiB): profiles/TAG_*.txt + traffic.json, then drop the large reports
+# except the two whose source pages are read here
+python scripts/ncu_to_traffic.py $TAG > gpurun_out/${TAG}_ncu_to_traffic.log 2>&1
+mkdir -p gpurun_out/profiles_$TAG
+cp profiles/${TAG}_*.txt profiles/traffic.json gpurun_out/profiles_$TAG/
+for f in gpurun_out/cap_${TAG}_*.ncu-rep; do
+  case $f in *knn_tc.ncu-rep|*configs_box_rearrangement_4M.ncu-rep) ;; *) rm -f $f ;; esac
+done
+# launch list of the default bench command (per-launch times are cold-cache and serialised: shares, not absolutes)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-planners > gpurun_out/${TAG}_launches_bench.log 2>&1
+tail -1 gpurun_out/${TAG}_launches_bench.log | cut -c1-300
