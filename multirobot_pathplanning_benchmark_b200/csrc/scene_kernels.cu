@@ -31,6 +31,8 @@ namespace mrb {
 
 constexpr int TILE = 32;
 constexpr int MAX_WARPS = 4;  // warps cooperating on one tile of 32 configurations: 2 or 4 (template parameter)
+constexpr int LAT_WARPS = 8;  // ... and on the ONE tile of a single query (the reference planners' call pattern): the broadphase
+                              // records and the kinematic chains are split eight ways -- latency, not throughput
 constexpr unsigned FULL = 0xffffffffu;
 
 // The one dynamic shared-memory window of every kernel in this file.  It is declared at file scope so
@@ -72,16 +74,18 @@ constexpr int CFG_MISC = 64 + 32 + 8;
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-// kind: 0 = configuration kernel (single pass), 1 = edge kernel, 2 = configuration kernel with two-phase tiles
+// kind: 0 = configuration kernel (single pass), 1 = edge kernel, 2 = configuration kernel with two-phase tiles,
+// 3 = configuration kernel (single pass) with LAT_WARPS warps on one tile (single queries), 4 = the same for the edge kernel
 __host__ __device__ inline size_t smem_layout(int blob_words, int D, int world_words, int n_shapes, int kind, size_t* off) {
-    const bool edges = kind == 1, pool = kind == 2;
+    const bool edges = kind == 1 || kind == 4, pool = kind == 2;
+    const int queue_warps = kind >= 3 ? LAT_WARPS : MAX_WARPS;
     size_t o = 0;
     off[0] = o; o = align16(o + size_t(blob_words) * 4);
     off[1] = o; o = align16(o + size_t(TILE) * D * 4);
     off[2] = o; o = align16(o + (edges ? 0 : size_t(TILE) * D * 4));  // second configuration buffer: configuration kernel only
     off[3] = o; o = align16(o + size_t(world_words) * TILE * 4);
     off[4] = o; o = align16(o + size_t(2) * TILE * 4);
-    off[5] = o; o = align16(o + size_t(MAX_WARPS) * QCAP_WORDS * 4);
+    off[5] = o; o = align16(o + size_t(queue_warps) * QCAP_WORDS * 4);
     off[6] = o; o = align16(o + size_t(n_shapes));
     off[7] = o; o = align16(o + 3 * 8);
     off[8] = o; o = align16(o + (edges ? EDGE_MISC * 4 : pool ? CFG_MISC * 4 : 0));
@@ -708,7 +712,7 @@ __device__ __noinline__ float full_tile_call(int blob_words, int D, int world_wo
 template <int WARPS, bool TWO_PHASE, int MINB = 16 / WARPS>
 __global__ void __launch_bounds__(TILE * WARPS, MINB) check_configs_kernel(ConfigParams p) {
     constexpr int THREADS = TILE * WARPS;
-    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, TWO_PHASE ? 2 : 0);
+    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, TWO_PHASE ? 2 : WARPS > MAX_WARPS ? 3 : 0);
     stage_scene(sm, p.blob, p.blob_words, p.n_shapes, p.rule, THREADS);
 
     const int D = p.D;
@@ -877,7 +881,7 @@ template <int WARPS>
 __global__ void __launch_bounds__(TILE * WARPS, 16 / WARPS) check_edges_kernel(EdgeParams p) {
     constexpr int THREADS = TILE * WARPS;
     constexpr int K = EDGE_SLOTS;
-    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, true);
+    const Smem sm = carve(smem_raw, p.blob_words, p.D, p.world_words, p.n_shapes, WARPS > MAX_WARPS ? 4 : 1);
     RobotRule none{};
     stage_scene(sm, p.blob, p.blob_words, p.n_shapes, none, THREADS);
 
@@ -1100,15 +1104,19 @@ cudaError_t launch_static_penetration(uint32_t* blob, cudaStream_t st) {
 cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
     const bool two = p.two_phase && !p.full_eval && !p.rule.enabled && !p.pen_out;
-    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, two ? 2 : 0);
     const int64_t n_tiles = (p.B + TILE - 1) / TILE;
+    static const bool lat_off = getenv("MRB200_NO_LATENCY_KERNEL") != nullptr;   // measurement aid
+    const bool latency = n_tiles == 1 && !two && !lat_off;
+    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, two ? 2 : latency ? 3 : 0);
 #define MRB_LAUNCH_CONFIGS(W, ...)                                                      \
     do {                                                                                \
         int grid = grid_for(check_configs_kernel<W, __VA_ARGS__>, 32 * W, smem);        \
         if (grid > n_tiles) grid = (int)n_tiles;                                        \
         check_configs_kernel<W, __VA_ARGS__><<<grid, 32 * W, smem, st>>>(p);            \
     } while (0)
-    if (warps_per_tile(p.world_words) == 4) {
+    if (latency) {
+        MRB_LAUNCH_CONFIGS(LAT_WARPS, false);
+    } else if (warps_per_tile(p.world_words) == 4) {
         const bool three = 4 * (smem + 1024) > 228 * 1024;   // shared memory admits three CTAs per SM at most
         if (two && three) MRB_LAUNCH_CONFIGS(4, true, 3);
         else if (two) MRB_LAUNCH_CONFIGS(4, true);
@@ -1124,10 +1132,16 @@ cudaError_t launch_check_configs(const ConfigParams& p, cudaStream_t st) {
 
 cudaError_t launch_check_edges(const EdgeParams& p, cudaStream_t st) {
     if (p.E <= 0) return cudaSuccess;
-    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, 1);
+    static const bool lat_off = getenv("MRB200_NO_LATENCY_KERNEL") != nullptr;   // measurement aid
+    const bool latency = p.E <= 2 && !lat_off;    // single edge queries of the reference planners: eight warps per tile
+    const size_t smem = scene_smem_bytes(p.blob_words, p.D, p.world_words, p.n_shapes, latency ? 4 : 1);
     cudaError_t err = cudaMemsetAsync(p.counter, 0, sizeof(int), st);
     if (err != cudaSuccess) return err;
-    if (warps_per_tile(p.world_words) == 4) {
+    if (latency) {
+        int grid = grid_for(check_edges_kernel<LAT_WARPS>, 32 * LAT_WARPS, smem);
+        if (grid > p.E) grid = (int)p.E;
+        check_edges_kernel<LAT_WARPS><<<grid, 32 * LAT_WARPS, smem, st>>>(p);
+    } else if (warps_per_tile(p.world_words) == 4) {
         int grid = grid_for(check_edges_kernel<4>, 128, smem);
         if (grid > p.E) grid = (int)p.E;
         check_edges_kernel<4><<<grid, 128, smem, st>>>(p);
