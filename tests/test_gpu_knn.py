@@ -96,12 +96,15 @@ def test_radius_inclusive_and_scalar(knn):
     assert off[-1].item() == 0
 
 
-@pytest.mark.parametrize("metric,R", [("max_euclidean", 4), ("max_euclidean", 2), ("euclidean", 1), ("max_euclidean", 3)])
+@pytest.mark.parametrize("metric,R", [("max_euclidean", 4), ("max_euclidean", 2), ("euclidean", 1), ("max_euclidean", 3),
+                                      ("max_euclidean", 6), ("max_euclidean", 8)])
 def test_tensor_core_path_equals_exact_path(knn, metric, R):
-    """tcgen05 candidates + fp64 re-rank must return exactly what the fp64 CUDA-core path returns."""
+    """tcgen05 candidates + fp64 re-rank must return exactly what the fp64 CUDA-core path returns (one to four robots:
+    the batch-load epilogue; six and eight robots of three joints: the generic 16-column epilogue)."""
     rng = np.random.default_rng(11 + R)
-    D = 6 * R if R > 1 else 24
-    sl = [[6 * r, 6 * r + 6] for r in range(R)] if R > 1 else None
+    dof = 6 if R <= 4 else 3
+    D = dof * R if R > 1 else 24
+    sl = [[dof * r, dof * r + dof] for r in range(R)] if R > 1 else None
     N, Q, k = 30011, 1531, 33
     corpus = rng.uniform(-3.2, 3.2, (N, D))
     queries = np.vstack([corpus[rng.choice(N, Q // 2, replace=False)], rng.uniform(-3.2, 3.2, (Q - Q // 2, D))])
@@ -207,6 +210,21 @@ def test_radius_at_baseline_size(knn):
         assert np.array_equal(dist[off[j]:off[j + 1]], d[want])
 
 
+@pytest.mark.parametrize("metric", ["max_euclidean", "euclidean"])
+def test_tensor_core_path_with_many_k_steps(knn, metric):
+    """D = 64: four robots of 16 joints need 12 K steps, euclidean needs 9 -- more than the MMA issuers keep in registers
+    (they then read their issue table from shared memory); tensor path == exact path"""
+    rng = np.random.default_rng(17)
+    D, N, Q, k = 64, 20_011, 700, 20
+    sl = [[16 * r, 16 * r + 16] for r in range(4)] if metric == "max_euclidean" else None
+    corpus = rng.uniform(-1.5, 1.5, (N, D))
+    queries = np.vstack([corpus[rng.choice(N, Q // 2, replace=False)], rng.uniform(-1.5, 1.5, (Q - Q // 2, D))])
+    c, q = torch.from_numpy(corpus).cuda(), torch.from_numpy(queries).cuda()
+    i_t, d_t = knn.batch_knn(q, c, sl, metric, k, mode="tensor")
+    i_e, d_e = knn.batch_knn(q, c, sl, metric, k, mode="exact")
+    assert torch.equal(i_t, i_e) and torch.equal(d_t, d_e)
+
+
 def test_radius_and_knn_at_the_largest_dimension(knn):
     """D = 64 (KNN_MAX_D): the radius kernels' corpus tiles need more than the default 48 KB of dynamic shared memory"""
     rng = np.random.default_rng(9)
@@ -226,14 +244,15 @@ def test_radius_and_knn_at_the_largest_dimension(knn):
             assert np.array_equal(i_k.cpu().numpy()[j], OA.knn_indices(OA.batch_config_dist(queries[j], corpus, np.array(sl), metric), 9))
 
 
-@pytest.mark.parametrize("metric,R", [("max_euclidean", 4), ("max_euclidean", 2), ("euclidean", 1)])
+@pytest.mark.parametrize("metric,R", [("max_euclidean", 4), ("max_euclidean", 2), ("euclidean", 1), ("max_euclidean", 6)])
 @pytest.mark.parametrize("inclusive", [False, True])
 def test_radius_tensor_path_equals_exact_path(knn, metric, R, inclusive):
     """r-disc search on the tcgen05 candidate generator + exact fp64 filter returns exactly what the fp64 kernels return:
     scalar and per-row radii, rows that overflow the candidate buffer (answered by the exact kernels), empty rows."""
     rng = np.random.default_rng(21 + R)
-    D = 6 * R if R > 1 else 24
-    sl = [[6 * r, 6 * r + 6] for r in range(R)] if R > 1 else None
+    dof = 6 if R <= 4 else 4
+    D = dof * R if R > 1 else 24
+    sl = [[dof * r, dof * r + dof] for r in range(R)] if R > 1 else None
     N, Q = 40_003, 3001
     corpus = rng.uniform(-3.2, 3.2, (N, D))
     queries = np.vstack([corpus[rng.choice(N, Q // 2, replace=False)], rng.uniform(-3.2, 3.2, (Q - Q // 2, D))])
