@@ -158,11 +158,17 @@ def test_edge_windows_and_explicit_N(be):
     assert chk.max() <= 23
 
 
-def test_for_robot_rule(be):
-    """A6: is_collision_free_for_robot (rai_base_env.py:515-615)."""
-    slot, sc, cs, kw = be.scenes["box_rearrangement"]
-    rel = np.array([1 if sc.robot_of_shape(n) == "a1_" else 0 for n in cs.shape_names], np.uint8)
-    oth = np.array([1 if sc.robot_of_shape(n) == "a2_" else 0 for n in cs.shape_names], np.uint8)
+@pytest.mark.parametrize("name", list(SCENES))
+def test_for_robot_rule(be, name):
+    """A6: is_collision_free_for_robot (rai_base_env.py:515-615) on every scene: the first robot is the robot asked about,
+    every other robot counts as `other` (contacts that involve neither the robot nor only other robots are ignored)."""
+    slot, sc, cs, kw = be.scenes[name]
+    robots = sorted({sc.robot_of_shape(n) for n in cs.shape_names} - {None, ""})
+    if len(robots) < 2:
+        pytest.skip("single-robot scene")
+    me = robots[0]
+    rel = np.array([1 if sc.robot_of_shape(n) == me else 0 for n in cs.shape_names], np.uint8)
+    oth = np.array([1 if sc.robot_of_shape(n) not in (me, None, "") else 0 for n in cs.shape_names], np.uint8)
     q = uniform_configs(sc, 40000, 30)
     got = be.check_configs_for_robot(slot, torch.from_numpy(q).cuda(), rel, oth).cpu().numpy()
     ofree, open_, omind = O.check_configs(cs.blob64, q.astype(np.float64), rel=rel, oth=oth, nthreads=O.max_threads())
@@ -170,6 +176,9 @@ def test_for_robot_rule(be):
     assert np.array_equal(got[clear], ofree[clear])
     plain = be.check_configs(slot, torch.from_numpy(q).cuda()).cpu().numpy()
     assert (got >= plain).all() and got.sum() > plain.sum()
+    # the single-query entry point (eight-warp kernel) gives the same flags
+    few = be.query_configs_host(slot, q[:7], None, rel, oth)
+    assert np.array_equal(np.asarray(few).astype(bool), got[:7].astype(bool))
 
 
 @pytest.mark.parametrize("name,parent,child", [("box_rearrangement", "a1_ur_vacuum", "obj11"), ("2d_handover", "a1", "obj1"),
