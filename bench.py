@@ -558,7 +558,7 @@ def main():
                 "d2h_bytes_per_step": world * B, "steps": e2e_steps, "timing": "CUDA events on the calling stream (which waits for the copy streams) around "
                 "calls that return after the flags have landed in host memory, max over ranks",
                 "h2d_only_gbs_per_rank_min": h2d_gbs_min, "numa": numa, "h2d_needed_gbs_per_rank_at_value": value / world * D * 4 / 1e9,
-                "path": "pinned host -> H2D -> check_configs -> D2H, 512k-config chunks on 2 streams"},
+                "path": "mrb200_check_configs_host: pinned host -> H2D -> check_configs -> D2H, 256k-config chunks on 3 side streams of the library"},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
     }
     if strong_sweep is not None:

@@ -111,6 +111,13 @@ int mrb200_query_edges_host(mrb200_scene_t* scene, int slot, const float* q1_hos
                             double resolution, const int32_t* N_host, int32_t n_start, int32_t n_max,
                             int include_endpoints, float tol, uint8_t* free_host, int32_t* first_pos_host,
                             mrb200_stream_t stream);
+/* Whole sample batches with HOST buffers (BaseProblem.is_collision_free over an array of samples, e.g. the validation
+ * of a PRM sample batch, P/planners/prm/prm_graph.py / collision_free_sampler.py:99-143): the batch is cut into chunks of
+ * `chunk` configurations (<= 0: 262144) that overlap H2D copy, kernel and D2H read-back on side streams owned by the
+ * handle.  Pinned (or cudaHostRegister-ed) buffers are copied from / to directly; pageable ones are bounced through
+ * pinned staging.  Returns after every flag has landed in free_host; later work on `stream` is ordered behind it. */
+int mrb200_check_configs_host(mrb200_scene_t* scene, int slot, const float* q_host /*[B, D]*/, int64_t B, float tol,
+                              uint8_t* free_host /*[B]*/, int64_t chunk, mrb200_stream_t stream);
 /* Asynchronous edge batches with HOST buffers -- the seam behind env.py's speculation of a PRM / EIT* node's candidate
  * edges (P/planners/prm/prm_graph.py:675 checks them lazily, one call each, right after get_neighbors :389-549 has
  * named them all).  submit: inputs are copied into a pinned buffer owned by the handle, H2D + kernel + D2H are queued on

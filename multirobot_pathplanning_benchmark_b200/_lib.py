@@ -41,6 +41,7 @@ SIGNATURES = {
     "mrb200_query_configs_host": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_float, c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "mrb200_query_edges_host": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int32, C.c_int,
                                           C.c_float, c_vp, c_vp, c_vp]),
+    "mrb200_check_configs_host": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.c_float, c_vp, C.c_int64, c_vp]),
     "mrb200_submit_edges_host": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int64, C.c_double, c_vp, C.c_int, C.c_float,
                                            C.POINTER(C.c_int64), c_vp]),
     "mrb200_collect_edges_host": (C.c_int, [c_vp, C.c_int64, C.c_int64, c_vp, c_vp]),

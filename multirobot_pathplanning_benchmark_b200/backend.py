@@ -303,35 +303,22 @@ class SceneBackend:
 
 
 def check_configs_host(be: SceneBackend, slot: int, q_host: torch.Tensor, out_host: torch.Tensor,
-                       chunk: int = 1 << 19, state: Optional[dict] = None) -> None:
-    """Host-buffer entry point (what a CPU-side caller of the reference API uses): q_host
-    [B, D] float32 and out_host [B] uint8, both pinned.  Copies, kernels and read-backs of
-    consecutive chunks overlap on the side streams; returns after everything has landed in out_host (host-side
-    synchronisation of the side streams -- a CPU caller may read out_host right away)."""
+                       chunk: int = 1 << 18, state: Optional[dict] = None, tol: Optional[float] = None) -> None:
+    """Host-buffer entry point for whole sample batches (what a CPU-side caller of the reference API uses): q_host
+    [B, D] float32 and out_host [B] uint8, contiguous host tensors (pinned ones are copied from / to directly).  One
+    call of `mrb200_check_configs_host`: the library overlaps the H2D copy, the kernel and the read-back of consecutive
+    chunks on its own side streams and returns after every flag has landed in out_host.  (`state` is accepted for
+    callers of the round-2 Python loop and ignored.)"""
     if q_host.is_cuda or out_host.is_cuda:
         raise ValueError("host tensors expected")
+    if q_host.dtype != torch.float32 or out_host.dtype != torch.uint8 or not q_host.is_contiguous() or not out_host.is_contiguous():
+        raise ValueError("q_host must be contiguous float32 [B, D], out_host contiguous uint8 [B]")
     B, D = q_host.shape
-    dev = be.device
-    st = state if state is not None else {}
-    if st.get("key") != (chunk, D, str(dev)):
-        st["key"] = (chunk, D, str(dev))
-        st["streams"] = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-        st["q"] = [torch.empty(chunk, D, dtype=torch.float32, device=dev) for _ in range(2)]
-        st["o"] = [torch.empty(chunk, dtype=torch.uint8, device=dev) for _ in range(2)]
-    cur = torch.cuda.current_stream(dev)
-    for s in st["streams"]:
-        s.wait_stream(cur)
-    for i, start in enumerate(range(0, B, chunk)):
-        n = min(chunk, B - start)
-        k = i & 1
-        with torch.cuda.stream(st["streams"][k]):
-            dq = st["q"][k][:n]
-            dq.copy_(q_host[start:start + n], non_blocking=True)
-            be.check_configs(slot, dq, out=st["o"][k][:n])
-            out_host[start:start + n].copy_(st["o"][k][:n], non_blocking=True)
-    for s in st["streams"]:
-        cur.wait_stream(s)
-        s.synchronize()
+    if D != be.compiled[slot].dof or out_host.numel() != B:
+        raise ValueError(f"q_host must be [B, {be.compiled[slot].dof}] and out_host [B]")
+    with torch.cuda.device(be.device):
+        _lib.check(be.lib.mrb200_check_configs_host(be.handle, slot, q_host.data_ptr(), B, -1.0 if tol is None else float(tol),
+                                                    out_host.data_ptr(), int(chunk), _stream(be.device)), "check_configs_host")
 
 
 def fp32_fma_peak_tflops(device=None, iters: int = 1 << 15, reps: int = 5) -> float:

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -77,6 +78,17 @@ struct mrb200_scene {
     unsigned char* stage_pin = nullptr;      // pinned + mapped host memory
     unsigned char* stage_pin_dev = nullptr;  // its device-side alias: tiny queries are read / written in place
     size_t stage_bytes = 0;
+    // chunk pipeline of mrb200_check_configs_host: HOST_PIPE side streams, each with device staging for one chunk of
+    // configurations and flags and (for pageable callers) a pinned bounce buffer; guarded by `mu`
+#ifndef MRB_HOST_PIPE
+#define MRB_HOST_PIPE 3
+#endif
+    static constexpr int HOST_PIPE = MRB_HOST_PIPE;
+    cudaStream_t pipe_stream[HOST_PIPE] = {};
+    cudaEvent_t pipe_start = nullptr, pipe_done[HOST_PIPE] = {};
+    unsigned char* pipe_dev[HOST_PIPE] = {};
+    unsigned char* pipe_pin[HOST_PIPE] = {};
+    size_t pipe_bytes = 0, pipe_pin_bytes = 0;
 };
 
 struct mrb200_abstract {
@@ -265,6 +277,13 @@ int mrb200_scene_destroy(mrb200_scene_t* sc) {
     cudaFreeHost(sc->stats_pin);
     cudaFree(sc->stage_dev);
     cudaFreeHost(sc->stage_pin);
+    for (int i = 0; i < mrb200_scene::HOST_PIPE; i++) {
+        if (sc->pipe_stream[i]) cudaStreamDestroy(sc->pipe_stream[i]);
+        if (sc->pipe_done[i]) cudaEventDestroy(sc->pipe_done[i]);
+        cudaFree(sc->pipe_dev[i]);
+        cudaFreeHost(sc->pipe_pin[i]);
+    }
+    if (sc->pipe_start) cudaEventDestroy(sc->pipe_start);
     for (auto& t : sc->tickets) {
         if (t.ev) cudaEventDestroy(t.ev);
         cudaFree(t.dev);
@@ -552,6 +571,113 @@ int mrb200_query_configs_host(mrb200_scene_t* sc, int slot, const float* q_host,
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "query_configs_host: D2H");
     memcpy(free_host, sc->stage_pin + qb, (size_t)B);
+    return MRB200_OK;
+}
+
+// Large host batches: the batch is cut into chunks that travel H2D, through the configuration kernel and back D2H on
+// HOST_PIPE side streams, so the copy of one chunk overlaps the kernel and the read-back of its neighbours.  With pinned
+// caller buffers the copies go straight from / to them; pageable buffers are bounced through pinned staging (then the
+// host memcpy is the limit).  Returns after every flag has landed in free_host.  (Round 2 ran this loop in Python over
+// torch streams: ~45 us of interpreter time per chunk limit the chunk size to 256k configurations and the pipeline's tail
+// to a 0.17 ms kernel; here a chunk costs three asynchronous driver calls.)
+int mrb200_check_configs_host(mrb200_scene_t* sc, int slot, const float* q_host, int64_t B, float tol, uint8_t* free_host,
+                              int64_t chunk, mrb200_stream_t stream) {
+    const ModeSlot* s = get_slot(sc, slot);
+    if (!s) return fail(MRB200_ERR_ARG, "check_configs_host: empty mode slot %d", slot);
+    if (B < 0 || (B && (!q_host || !free_host))) return fail(MRB200_ERR_ARG, "check_configs_host: bad argument");
+    if (B == 0) return MRB200_OK;
+    if (chunk <= 0) chunk = 1 << 18;
+    chunk = (chunk + 31) / 32 * 32;
+    if (chunk > B) chunk = (B + 31) / 32 * 32;
+    constexpr int NP = mrb200_scene::HOST_PIPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lock(sc->mu);
+    cudaError_t e = cudaSuccess;
+    if (!sc->pipe_start) {
+        e = cudaEventCreateWithFlags(&sc->pipe_start, cudaEventDisableTiming);
+        for (int i = 0; i < NP && e == cudaSuccess; i++) {
+            e = cudaStreamCreateWithFlags(&sc->pipe_stream[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sc->pipe_done[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "check_configs_host: streams");
+    }
+    const size_t qb = up16((size_t)chunk * s->D * 4), need = qb + up16((size_t)chunk);
+    if (need > sc->pipe_bytes) {
+        for (int i = 0; i < NP; i++) {
+            cudaStreamSynchronize(sc->pipe_stream[i]);
+            cudaFree(sc->pipe_dev[i]);
+            sc->pipe_dev[i] = nullptr;
+        }
+        sc->pipe_bytes = 0;
+        for (int i = 0; i < NP; i++) {
+            e = cudaMalloc(&sc->pipe_dev[i], need);
+            if (e != cudaSuccess) return cuda_fail(e, "check_configs_host: cudaMalloc");
+        }
+        sc->pipe_bytes = need;
+    }
+    // pinned (or registered) caller memory can be copied asynchronously; anything else goes through a pinned bounce buffer
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool direct = pinned(q_host) && pinned(free_host);
+    if (!direct && need > sc->pipe_pin_bytes) {
+        for (int i = 0; i < NP; i++) {
+            cudaStreamSynchronize(sc->pipe_stream[i]);
+            cudaFreeHost(sc->pipe_pin[i]);
+            sc->pipe_pin[i] = nullptr;
+        }
+        sc->pipe_pin_bytes = 0;
+        for (int i = 0; i < NP; i++) {
+            e = cudaHostAlloc(&sc->pipe_pin[i], need, cudaHostAllocDefault);
+            if (e != cudaSuccess) return cuda_fail(e, "check_configs_host: cudaHostAlloc");
+        }
+        sc->pipe_pin_bytes = need;
+    }
+    // the side streams start behind the caller's stream
+    e = cudaEventRecord(sc->pipe_start, st);
+    for (int i = 0; i < NP && e == cudaSuccess; i++) e = cudaStreamWaitEvent(sc->pipe_stream[i], sc->pipe_start, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "check_configs_host: start");
+    mrb::RobotRule rule{};
+    int64_t done_upto[NP];   // pageable callers: first row / rows of the chunk whose flags wait in pipe_pin[k]
+    int64_t done_rows[NP];
+    for (int i = 0; i < NP; i++) done_upto[i] = done_rows[i] = 0;
+    int k = 0;
+    for (int64_t first = 0; first < B; first += chunk, k = (k + 1) % NP) {
+        const int64_t n = std::min<int64_t>(chunk, B - first);
+        cudaStream_t ps = sc->pipe_stream[k];
+        float* qd = (float*)sc->pipe_dev[k];
+        uint8_t* fd = sc->pipe_dev[k] + qb;
+        if (direct) {
+            e = cudaMemcpyAsync(qd, q_host + first * s->D, (size_t)n * s->D * 4, cudaMemcpyHostToDevice, ps);
+        } else {
+            // the bounce buffer of this stream is free once its previous chunk has come back
+            e = cudaStreamSynchronize(ps);
+            if (e == cudaSuccess && done_rows[k]) memcpy(free_host + done_upto[k], sc->pipe_pin[k] + qb, (size_t)done_rows[k]);
+            done_rows[k] = 0;
+            memcpy(sc->pipe_pin[k], q_host + first * s->D, (size_t)n * s->D * 4);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(qd, sc->pipe_pin[k], (size_t)n * s->D * 4, cudaMemcpyHostToDevice, ps);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "check_configs_host: H2D");
+        const int rc = check_configs_impl(sc, slot, qd, n, tol, fd, nullptr, 0, rule, (mrb200_stream_t)ps, /*allow_bulk=*/true);
+        if (rc) return rc;
+        if (direct) {
+            e = cudaMemcpyAsync(free_host + first, fd, (size_t)n, cudaMemcpyDeviceToHost, ps);
+        } else {
+            e = cudaMemcpyAsync(sc->pipe_pin[k] + qb, fd, (size_t)n, cudaMemcpyDeviceToHost, ps);
+            done_upto[k] = first;
+            done_rows[k] = n;
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "check_configs_host: D2H");
+    }
+    for (int i = 0; i < NP; i++) {
+        e = cudaEventRecord(sc->pipe_done[i], sc->pipe_stream[i]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, sc->pipe_done[i], 0);   // later work on the caller's stream is ordered behind
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sc->pipe_stream[i]);
+        if (e != cudaSuccess) return cuda_fail(e, "check_configs_host: finish");
+        if (!direct && done_rows[i]) memcpy(free_host + done_upto[i], sc->pipe_pin[i] + qb, (size_t)done_rows[i]);
+    }
     return MRB200_OK;
 }
 

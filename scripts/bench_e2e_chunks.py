@@ -12,7 +12,7 @@ B = 4_194_304
 lim = sc.limits()
 q = torch.from_numpy(np.random.RandomState(0).uniform(lim[0], lim[1], (B, sc.dof)).astype(np.float32)).pin_memory()
 out = torch.empty(B, dtype=torch.uint8).pin_memory()
-for chunk in (1 << 19, 1 << 18, 1 << 17, 1 << 16, 1 << 15):
+for chunk in (1 << 19, 1 << 18, 1 << 17, 1 << 16, 1 << 15, 1 << 14):
     st = {}
     for _ in range(2): check_configs_host(be, 0, q, out, chunk=chunk, state=st)
     torch.cuda.synchronize()

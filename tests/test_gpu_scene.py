@@ -253,6 +253,26 @@ def test_host_buffer_queries_equal_device_buffer_calls(be):
         be.query_configs_host(slot, q[:, :5])
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_chunked_host_batches_equal_device_flags(be, pinned):
+    """mrb200_check_configs_host (whole sample batches from host memory, chunks pipelined on the library's side streams):
+    the same flags as the device-buffer call, for pinned and pageable buffers, ragged last chunks, and a stream of calls"""
+    from multirobot_pathplanning_benchmark_b200.backend import check_configs_host
+    slot, sc, cs, kw = be.scenes["box_rearrangement"]
+    for B, chunk in ((100_003, 1 << 14), (40_000, 1 << 17), (33, 32), (5 * 4096, 4096)):
+        q = torch.from_numpy(uniform_configs(sc, B, 77))
+        out = torch.full((B,), 7, dtype=torch.uint8)
+        if pinned:
+            q, out = q.pin_memory(), out.pin_memory()
+        want = be.check_configs(slot, q.cuda()).cpu()
+        for _ in range(2):
+            check_configs_host(be, slot, q, out, chunk=chunk)
+            assert torch.equal(out, want)
+            out.fill_(7)
+    with pytest.raises(ValueError):
+        check_configs_host(be, slot, torch.zeros(4, sc.dof + 1), torch.zeros(4, dtype=torch.uint8))
+
+
 def test_edge_kernel_corner_cases(be):
     """multi-edge tiles: degenerate edges (N = 2: no interior point), empty windows, a single edge, mixed explicit N,
     windows beyond N, batches smaller than one tile and far larger than the grid -- all against the oracle"""
