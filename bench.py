@@ -553,7 +553,8 @@ def main():
         "metric": METRIC, "value": value, "unit": "configs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {**config_block(args, scene_name, B, world, D, cs), "free_fraction": free_frac},
+        "config": config_block(args, scene_name, B, world, D, cs),   # the same keys and values as the reference arm's line
+        "free_fraction": free_frac,
         "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": world * B * D * 4,
                 "d2h_bytes_per_step": world * B, "steps": e2e_steps, "timing": "CUDA events on the calling stream (which waits for the copy streams) around "
                 "calls that return after the flags have landed in host memory, max over ranks",
