@@ -32,9 +32,16 @@ for t in range(6):
                 w = I(off + 2 * i)
                 recs.append((t, wo2shape[w & 0xffff], wo2shape[w >> 16]))
 print(name, "records", n_rec_total, "moving-moving", len(recs))
+SEG = int(sys.argv[2]) if len(sys.argv) > 2 else 0    # 0: one group per frame pair; S > 0: frames of a robot merged into S segments
+rob = b[I(S.H_OFF_SHAPE_ROBOT): I(S.H_OFF_SHAPE_ROBOT) + ns].astype(np.int64)
+def seg_of(i):
+    if SEG == 0:
+        return int(fid[i])
+    fr = sorted({int(fid[j]) for j in range(nm) if rob[j] == rob[i]})
+    return (int(rob[i]), fr.index(int(fid[i])) * SEG // len(fr))
 groups = {}
 for (t, x, y) in recs:
-    groups.setdefault((t, int(fid[x]), int(fid[y])), []).append((x, y))
+    groups.setdefault((t, seg_of(x), seg_of(y)), []).append((x, y))
 sizes = [len(v) for v in groups.values()]
 print("groups", len(groups), "mean size", np.mean(sizes), "max", max(sizes))
 rng = np.random.default_rng(0); lim = sc.limits()
