@@ -71,5 +71,40 @@ def test_records_cover_every_reachable_pair(name):
             n_queued += 1
             assert ((a, c) in recs) != (frozenset((a, c)) in skipped), "every dynamic pair is either recorded or proven unreachable"
     assert n_queued == len(recs) + len(skipped)
-    if name in ("2d_handover", "mobile_wall_four"):   # translating bases reach everywhere
+    if name == "2d_handover":   # translating bases reach everywhere, every shape lives at the same height
         assert not skipped
+
+
+def test_vertically_separated_pairs_never_touch():
+    """mobile_wall_four: the bases translate in the plane, so the reach balls prune nothing -- but shapes whose chains only
+    move in the plane keep their world z, and pairs whose z intervals are apart (the bases 4 cm above the floor slab, the
+    first arm links above the bricks ...) get no broadphase record.  Their EXACT distance (the oracle's primitive routines)
+    stays positive for joint vectors far outside the limits too."""
+    mk, kw = SCENES["mobile_wall_four"]
+    sc = mk()
+    cs = S.compile_blob(sc, kw["tol"])
+    idx = {n: i for i, n in enumerate(cs.shape_names)}
+    skipped = {frozenset((idx[a], idx[c])) for a, c in cs.unreachable_pairs}
+    assert any("base" in a + c and "table" in a + c for a, c in cs.unreachable_pairs)
+    b = cs.blob64
+    ns = cs.n_moving + cs.n_static
+    offS = int(b[S.H_OFF_SHAPES])
+    rad = b[offS: offS + ns * S.SHAPE_WORDS].reshape(ns, S.SHAPE_WORDS)[:, 3].view(np.float64)
+    typed = []
+    for t in range(6):
+        n, off = int(b[S.H_N_PAIRS + t]), int(b[S.H_OFF_PAIRS + t])
+        for i in range(n):
+            pk = int(b[off + i])
+            a, c = pk & 0xffff, (pk >> 16) & 0xfff
+            if frozenset((a, c)) in skipped:
+                typed.append((t, a, c))
+    assert len(typed) == len(skipped) >= 8
+    rng = np.random.default_rng(3)
+    lim = sc.limits()
+    qs = np.concatenate([rng.uniform(lim[0], lim[1], (400, sc.dof)), rng.uniform(-9.0, 9.0, (400, sc.dof))])
+    closest = np.inf
+    for q in qs:
+        W = O.world_shapes(b, q, ns)
+        for t, a, c in typed:
+            closest = min(closest, O.pair_distance(t, W[a], W[c], rad[a] + rad[c]))
+    assert closest > 4 * S.CULL_SLACK, f"a vertically separated pair comes within {closest} of touching"
