@@ -453,6 +453,29 @@ class CompiledScene:
     unreachable_pairs: List[Tuple[str, str]] = field(default_factory=list)  # collidable, but out of each other's reach
 
 
+_CHAIN_APART_CACHE: Dict[tuple, bool] = {}   # compile_blob: chain-neighbour pairs already analysed (the same for every mode)
+
+
+def _seg_seg_dist(p1, q1, p2, q2):
+    """distance between segments [p1, q1] and [p2, q2], row-wise ([n, 3] arrays; degenerate segments are points):
+    closest points by clamping the unconstrained solution (Ericson, Real-Time Collision Detection 5.1.9)"""
+    d1, d2, r = q1 - p1, q2 - p2, p1 - p2
+    a, e, f = (d1 * d1).sum(1), (d2 * d2).sum(1), (d2 * r).sum(1)
+    c, b = (d1 * r).sum(1), (d1 * d2).sum(1)
+    eps = 1e-18
+    denom = a * e - b * b
+    s_ = np.where(denom > eps, np.clip((b * f - c * e) / np.where(denom > eps, denom, 1.0), 0.0, 1.0), 0.0)
+    s_ = np.where(a > eps, s_, 0.0)
+    t_ = np.where(e > eps, (b * s_ + f) / np.where(e > eps, e, 1.0), 0.0)
+    s_lo = np.where(a > eps, np.clip(-c / np.where(a > eps, a, 1.0), 0.0, 1.0), 0.0)
+    s_hi = np.where(a > eps, np.clip((b - c) / np.where(a > eps, a, 1.0), 0.0, 1.0), 0.0)
+    s_ = np.where(t_ < 0.0, s_lo, np.where(t_ > 1.0, s_hi, s_))
+    t_ = np.clip(t_, 0.0, 1.0)
+    c1 = p1 + d1 * s_[:, None]
+    c2 = p2 + d2 * t_[:, None]
+    return np.linalg.norm(c1 - c2, axis=1)
+
+
 def compile_blob(scene: Scene, tol: float) -> CompiledScene:
     lay = scene.q_layout()
     X0 = scene.fk(scene.home())  # static frames: any q works
@@ -675,8 +698,94 @@ def compile_blob(scene: Scene, tol: float) -> CompiledScene:
         a, b = z_iv[x], z_iv[y]
         return a is not None and b is not None and (a[0] - b[1] > 4 * CULL_SLACK or b[0] - a[1] > 4 * CULL_SLACK)
 
+    # --- neighbours on a chain: a capsule / sphere pair whose relative pose depends on at most two hinge angles (a link
+    # against the link two joints up, a wrist capsule against the gripper body, the first links against shapes on the robot's
+    # static base) is evaluated EXACTLY on a grid over the full circle of those angles; with the Lipschitz bound of the
+    # motion between grid points its distance stays positive for every joint vector, so it gets no record.  Such pairs
+    # pass the bounding-sphere test for (nearly) every configuration -- 2 per arm on the UR10 scenes -- and each one is a
+    # narrowphase item per configuration that can never contribute.
+    chain_of = {}
+    for ci, (c0, c1) in enumerate(chain_rows):
+        for f in range(c0, c1):
+            chain_of[f] = (ci, c0)
+
+    _fkeys: Dict[int, tuple] = {}
+    _skeys: Dict[int, tuple] = {}
+
+    def frame_key(k: int) -> tuple:
+        if k not in _fkeys:
+            A = frame_rows[k][3]
+            _fkeys[k] = (frame_rows[k][1],) + tuple(round(float(v), 9) for v in A.R.reshape(-1)) + tuple(round(float(v), 9) for v in A.t)
+        return _fkeys[k]
+
+    def shape_key(i: int) -> tuple:
+        if i not in _skeys:
+            core, _, _, rad, data, _ = shape_rows[i]
+            _skeys[i] = (core, round(rad, 9)) + tuple(round(float(v), 9) for v in data[:6])
+        return _skeys[i]
+
+    def local_points(i: int):
+        core, fid, _, rad, data, _ = shape_rows[i]
+        if core == CORE_POINT:
+            return np.array([data[:3], data[:3]], dtype=np.float64), rad
+        if core == CORE_SEG:
+            return np.array([data[:3], data[3:6]], dtype=np.float64), rad
+        return None, rad
+
+    def chain_apart(x: int, y: int) -> bool:
+        fx = shape_rows[x][1]
+        fy = shape_rows[y][1] if y < n_mov else -1
+        if fy > fx:
+            x, y, fx, fy = y, x, fy, fx
+        if fx < 0 or shape_rows[x][0] > CORE_SEG or shape_rows[y][0] > CORE_SEG:
+            return False
+        ci, c0 = chain_of[fx]
+        first = c0 if fy < 0 else fy + 1          # joints first .. fx move x relative to y's frame (the world for static y)
+        if fx - first > 1 or fx < first or (fy >= 0 and chain_of[fy][0] != ci):
+            return False
+        joints = list(range(first, fx + 1))
+        if any(code_joint[frame_rows[k][1]] not in HINGE_AXIS for k in joints):
+            return False
+        px, rx_ = local_points(x)
+        py, ry_ = local_points(y)
+        key = (tuple(frame_key(k) for k in joints), shape_key(x), shape_key(y), fy < 0)
+        if key in _CHAIN_APART_CACHE:
+            return _CHAIN_APART_CACHE[key]
+        step = math.radians(0.25 if len(joints) == 1 else 1.0)
+        grids = np.meshgrid(*[np.arange(0.0, 2 * math.pi, step) for _ in joints], indexing="ij")
+        th = [g.reshape(-1) for g in grids]
+        n = th[0].size
+        # pose of frame fx relative to y's frame: product over the joints of A_k * Rot(axis_k, theta_k); the lever arm of
+        # a joint = distance of x's end points from the joint's axis point (its frame origin)
+        R = np.broadcast_to(np.eye(3), (n, 3, 3)).copy()
+        t = np.zeros((n, 3))
+        origins = []
+        for k, a in zip(joints, th):
+            A = frame_rows[k][3]
+            t = t + R @ A.t
+            R = R @ A.R
+            origins.append(t.copy())
+            ax = HINGE_AXIS[code_joint[frame_rows[k][1]]]
+            c, s_ = np.cos(a), np.sin(a)
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            J = np.eye(3)[None] + s_[:, None, None] * K[None] + (1 - c)[:, None, None] * (K @ K)[None]
+            R = R @ J
+        a0 = np.einsum("nij,j->ni", R, px[0]) + t
+        a1 = np.einsum("nij,j->ni", R, px[1]) + t
+        if fy < 0:      # static partner: its data are world coordinates, and so is the chain's root transform
+            b0, b1 = py[0][None], py[1][None]
+        else:
+            b0, b1 = py[0][None], py[1][None]
+        d = _seg_seg_dist(a0, a1, np.broadcast_to(b0, a0.shape), np.broadcast_to(b1, a0.shape)) - rx_ - ry_
+        lever = sum(float(np.max(np.maximum(np.linalg.norm(a0 - o, axis=1), np.linalg.norm(a1 - o, axis=1)))) + rx_ for o in origins)
+        ok = bool(d.min() - 0.5 * step * lever > 4 * CULL_SLACK)
+        _CHAIN_APART_CACHE[key] = ok
+        return ok
+
     def never_meets(x: int, y: int, kind: int) -> bool:
         if vertically_apart(x, y):
+            return True
+        if chain_apart(x, y):
             return True
         if not any_bounded:
             return False
